@@ -1,0 +1,161 @@
+/* mjxb -- C ABI of the B200-native batched humanoid physics step.
+ *
+ * This is the drop-in boundary for the hot path that the reference drives through
+ *   src/envs.py:494-495   v_reset = jit(vmap(single_reset)); v_step = jit(vmap(single_step))
+ *   src/envs.py:108-113   single_pipeline_init  (mjx.make_data -> mjx.forward)
+ *   src/envs.py:345       mjx.step(sys, d)
+ *   mjx_humanoid_speed_test.py:48-57,88-93   vmap(make_data -> qvel[0]=v -> mjx.step -> qpos[0])
+ * Nothing like it exists in the reference (pure Python on JAX/MJX); each entry point below names the
+ * reference function it replaces.  INTEGRATION.md shows the XLA-FFI / ctypes binding a maintainer adds.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / jax types.
+ *   - every array argument of the *device* entry points is a CUDA device pointer owned by the caller,
+ *     row-major [n_env, k] float32 ("structure of arrays": one array per state field);
+ *     all work is enqueued on the caller's stream (`stream` is a cudaStream_t passed as void*);
+ *     no allocation, no host synchronisation inside reset/step.
+ *   - the *_host entry points take host pointers and do H2D -> kernel -> D2H themselves (synchronous).
+ *   - return value: 0 = ok, negative = MJXB_E* (argument / CUDA errors, reported synchronously).
+ *     Numerical trouble is reported asynchronously per env through `status` (bit flags below).
+ *   - mjxb_model is immutable after create; one model per device; thread-safe for distinct streams.
+ */
+#ifndef MJXB_H_
+#define MJXB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+#include "mjxb_model.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MJXB_ABI_VERSION 1
+
+#define MJXB_OK 0
+#define MJXB_EINVAL (-1)   /* bad argument (NULL pointer, n_env <= 0, size mismatch) */
+#define MJXB_EBLOB (-2)    /* model blob has wrong magic / version / size or exceeds compiled capacities */
+#define MJXB_ECUDA (-3)    /* CUDA runtime error (mjxb_last_cuda_error() has the text) */
+#define MJXB_ENOGPU (-4)   /* no CUDA device: there is deliberately no CPU fallback */
+#define MJXB_EUNSUPPORTED (-5)
+
+/* per-env status bits (int32 status[n_env], optional) */
+#define MJXB_STATUS_NAN 1            /* non-finite qacc / state produced */
+#define MJXB_STATUS_ROW_SPILL 2      /* candidate constraint rows exceeded the shared-memory tile; global scratch used */
+#define MJXB_STATUS_MAXITER 4        /* Newton/CG hit opt.iterations without meeting the tolerance */
+
+#define MJXB_AUX_DIM 9    /* src/envs.py:15  [flip,tx,ty,tz,close_count,stance_state,stance_last_change_time,last_pot,episode_step] */
+#define MJXB_MAXOBS 64
+
+/* EnvConfig (src/config.py:29-66) + the flip permutations create_env_functions derives (src/envs.py:49-74). */
+typedef struct mjxb_env_config {
+  float progress_weight, electricity_cost, stall_torque_cost, posture_penalty_weight;
+  float tall_height_threshold, tall_bonus_weight, target_threshold, target_dist;
+  float stance_time_reward_weight, random_joint_noise, random_vel_noise, initial_velocity_max;
+  float terminate_height, terminate_reward;
+  int32_t stop_frames, max_episode_steps, random_flip;
+  int32_t pelvis_body_id, head_body_id, touch_sensor_right_id, touch_sensor_left_id;
+  int32_t obs_dim;
+  int32_t act_perm[MJXB_MAXU];
+  float act_sign[MJXB_MAXU];
+  int32_t obs_perm[MJXB_MAXOBS];
+  float obs_sign[MJXB_MAXOBS];
+} mjxb_env_config;
+
+/* The persistent per-env state: the minimal replacement of `EnvState = (mjx.Data, AuxState)` (src/envs.py:13-17).
+ * Everything else the env reads from mjx.Data (xpos, xquat, sensordata, qfrc_actuator) is recomputed in the step. */
+typedef struct mjxb_state {
+  float* qpos;           /* [n_env, nq]  */
+  float* qvel;           /* [n_env, nv]  */
+  float* qacc_warmstart; /* [n_env, nv]  */
+  float* time;           /* [n_env]      */
+  float* aux;            /* [n_env, 9]   */
+} mjxb_state;
+
+/* Optional per-stage outputs for parity tests (any pointer may be NULL). Shapes use the model's static sizes. */
+typedef struct mjxb_debug {
+  float* xpos;            /* [n, nbody, 3] */
+  float* xquat;           /* [n, nbody, 4] */
+  float* qM;              /* [n, nv, nv]   dense symmetric */
+  float* qfrc_bias;       /* [n, nv] */
+  float* qfrc_passive;    /* [n, nv] */
+  float* qfrc_actuator;   /* [n, nv] */
+  float* qacc_smooth;     /* [n, nv] */
+  float* con_dist;        /* [n, ncon] */
+  float* con_pos;         /* [n, ncon, 3] */
+  float* con_normal;      /* [n, ncon, 3] */
+  float* efc_pos;         /* [n, nefc]  (0 for rows that are not candidates, as MJX masks them) */
+  float* efc_D;           /* [n, nefc] */
+  float* efc_aref;        /* [n, nefc] */
+  float* efc_force;       /* [n, nefc] */
+  int32_t* efc_active;    /* [n, nefc]  bit0: candidate (pos<0); bit1: active at the solution (Jaref<0) */
+  float* qacc;            /* [n, nv] */
+  float* qfrc_constraint; /* [n, nv] */
+  float* sensordata;      /* [n, nsensor] */
+  int32_t* solver_niter;  /* [n] */
+} mjxb_debug;
+
+typedef struct mjxb_model mjxb_model;
+
+int mjxb_abi_version(void);
+size_t mjxb_blob_sizeof(void);
+size_t mjxb_env_config_sizeof(void);
+const char* mjxb_strerror(int code);
+const char* mjxb_last_cuda_error(void);
+
+/* replaces mjx.put_model(m) + create_env_functions' closure over (sys, cfg, q0) (src/training_utils.py:105-112).
+ * `blob` is the POD produced by modelc.pack_blob (struct mjxb_model_blob); copied to `device`. */
+int mjxb_model_create(const void* blob, size_t blob_bytes, const mjxb_env_config* cfg, int device, mjxb_model** out);
+void mjxb_model_destroy(mjxb_model* m);
+/* nq, nv, nu, nbody, ncon, nefc, nsensor, obs_dim */
+int mjxb_model_dims(const mjxb_model* m, int32_t dims[8]);
+/* bytes of per-launch global scratch the library holds for constraint-row spills (allocated at create). */
+size_t mjxb_model_scratch_bytes(const mjxb_model* m);
+
+/* v_reset (src/envs.py:115-202,494): keys u32[n,2] (JAX threefry key data) -> state, obs[n,obs_dim]. */
+int mjxb_reset(const mjxb_model* m, int32_t n_env, const uint32_t* keys, mjxb_state out, float* obs,
+               int32_t* status, void* stream);
+
+/* v_step (src/envs.py:333-492,495): (state, action[n,nu]) -> state', obs, reward, terminated, truncated.
+ * `in` and `out` may alias field by field (in-place update). */
+int mjxb_step(const mjxb_model* m, int32_t n_env, mjxb_state in, const float* action, mjxb_state out,
+              float* obs, float* reward, float* terminated, float* truncated, int32_t* status, void* stream);
+
+/* v_step fused with the trainer's auto-reset glue (train_ppo.py:143-161): envs with max(terminated,truncated)>0
+ * are re-initialised from keys[n,2] inside the same launch; reward/terminated/truncated are the step's,
+ * state/obs are the merged ones; reset_mask[n] (u8, optional) reports which envs were reset. */
+int mjxb_step_autoreset(const mjxb_model* m, int32_t n_env, mjxb_state in, const float* action,
+                        const uint32_t* keys, mjxb_state out, float* obs, float* reward, float* terminated,
+                        float* truncated, uint8_t* reset_mask, int32_t* status, void* stream);
+
+/* mjx.step (src/envs.py:345; mjx_humanoid_speed_test.py:54) without the env layer: nsteps consecutive physics
+ * steps with a fixed ctrl[n,nu] (may be NULL = zeros), state advanced in place (aux is ignored).
+ * `dbg` (optional) receives the stage outputs of the LAST step's forward pass. */
+int mjxb_physics_step(const mjxb_model* m, int32_t n_env, mjxb_state io, const float* ctrl, int32_t nsteps,
+                      const mjxb_debug* dbg, int32_t* status, void* stream);
+
+/* mjx.forward (src/envs.py:112): forward dynamics only (no integration); writes qacc_warmstart, dbg. */
+int mjxb_forward(const mjxb_model* m, int32_t n_env, mjxb_state io, const float* ctrl, const mjxb_debug* dbg,
+                 int32_t* status, void* stream);
+
+/* mjx_humanoid_speed_test.py:48-57,88-93: for it in range(iters): pos = step(make_data with qvel[0]=vel[i]).qpos[0];
+ * acc += sum(pos). vel[n] in, pos[n] out (last iteration), device pointers. */
+int mjxb_speed_test(const mjxb_model* m, int32_t n_env, const float* vel, float* pos, int32_t iters, void* stream);
+
+/* Host-buffer variants (pinned or pageable host memory): H2D of the inputs, the launch, D2H of the outputs, sync.
+ * The device state stays resident in a library-owned arena bound to `m` (created on first use for n_env). */
+int mjxb_reset_host(mjxb_model* m, int32_t n_env, const uint32_t* keys_host, float* obs_host);
+int mjxb_step_host(mjxb_model* m, int32_t n_env, const float* action_host, float* obs_host, float* reward_host,
+                   float* terminated_host, float* truncated_host);
+int mjxb_step_autoreset_host(mjxb_model* m, int32_t n_env, const float* action_host, const uint32_t* keys_host,
+                             float* obs_host, float* reward_host, float* terminated_host, float* truncated_host);
+/* copy the resident arena state to / from host arrays (any pointer may be NULL) */
+int mjxb_state_get_host(mjxb_model* m, int32_t n_env, float* qpos, float* qvel, float* qacc_warmstart, float* time,
+                        float* aux);
+int mjxb_state_set_host(mjxb_model* m, int32_t n_env, const float* qpos, const float* qvel,
+                        const float* qacc_warmstart, const float* time, const float* aux);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MJXB_H_ */
