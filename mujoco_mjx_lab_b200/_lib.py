@@ -1,0 +1,92 @@
+"""ctypes loader of the C-ABI shared library (mujoco_mjx_lab_b200/libmjxb.so, built from csrc/ for sm_100a).
+
+There is no CPU fallback: a missing library or a missing GPU raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+from ._abi import DebugC, EnvConfigC, StateC
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmjxb.so")
+
+ERRORS = {0: "ok", -1: "invalid argument", -2: "bad model blob", -3: "CUDA error", -4: "no CUDA device (no CPU fallback)",
+          -5: "unsupported model"}
+
+# every symbol include/mjxb.h declares (tests check that the built library exports all of them)
+SYMBOLS = ("mjxb_abi_version", "mjxb_blob_sizeof", "mjxb_env_config_sizeof", "mjxb_strerror", "mjxb_last_cuda_error",
+           "mjxb_model_create", "mjxb_model_destroy", "mjxb_model_dims", "mjxb_model_scratch_bytes", "mjxb_reset", "mjxb_step",
+           "mjxb_step_autoreset", "mjxb_physics_step", "mjxb_forward", "mjxb_speed_test", "mjxb_reset_host", "mjxb_step_host",
+           "mjxb_step_autoreset_host", "mjxb_state_get_host", "mjxb_state_set_host")
+
+
+class MjxbError(RuntimeError):
+    pass
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/ -> libmjxb.so with nvcc for sm_100a (cross-compiles without a GPU)."""
+    csrc = os.path.join(_HERE, "csrc")
+    inc = os.path.join(_HERE, "..", "include")
+    srcs = [os.path.join(csrc, f) for f in ("mjxb_abi.cu", "mjxb_device.cuh")] + [os.path.join(inc, f) for f in ("mjxb.h", "mjxb_model.h")]
+    stale = force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
+    if stale:
+        r = subprocess.run(["make", "-C", csrc, "-B", "../libmjxb.so"], capture_output=True, text=True)
+        if verbose or r.returncode != 0:
+            print(r.stdout[-4000:], r.stderr[-4000:])
+        if r.returncode != 0:
+            raise MjxbError("nvcc build of libmjxb.so failed")
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MjxbError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(the CUDA extension is mandatory; there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    L.mjxb_abi_version.restype = C.c_int
+    L.mjxb_blob_sizeof.restype = C.c_size_t
+    L.mjxb_env_config_sizeof.restype = C.c_size_t
+    L.mjxb_model_scratch_bytes.restype = C.c_size_t
+    L.mjxb_model_scratch_bytes.argtypes = [C.c_void_p]
+    L.mjxb_strerror.restype = C.c_char_p
+    L.mjxb_strerror.argtypes = [C.c_int]
+    L.mjxb_last_cuda_error.restype = C.c_char_p
+    L.mjxb_model_create.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(EnvConfigC), C.c_int, C.POINTER(C.c_void_p)]
+    L.mjxb_model_destroy.argtypes = [C.c_void_p]
+    L.mjxb_model_destroy.restype = None
+    L.mjxb_model_dims.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
+    L.mjxb_launch_config.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
+    vp, i32 = C.c_void_p, C.c_int32
+    L.mjxb_reset.argtypes = [vp, i32, vp, StateC, vp, vp, vp]
+    L.mjxb_step.argtypes = [vp, i32, StateC, vp, StateC, vp, vp, vp, vp, vp, vp]
+    L.mjxb_step_autoreset.argtypes = [vp, i32, StateC, vp, vp, StateC, vp, vp, vp, vp, vp, vp, vp]
+    L.mjxb_physics_step.argtypes = [vp, i32, StateC, vp, i32, C.POINTER(DebugC), vp, vp]
+    L.mjxb_forward.argtypes = [vp, i32, StateC, vp, C.POINTER(DebugC), vp, vp]
+    L.mjxb_speed_test.argtypes = [vp, i32, vp, vp, i32, vp]
+    L.mjxb_reset_host.argtypes = [vp, i32, vp, vp]
+    L.mjxb_step_host.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+    L.mjxb_step_autoreset_host.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
+    L.mjxb_state_get_host.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+    L.mjxb_state_set_host.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+    if L.mjxb_abi_version() != 1:
+        raise MjxbError("libmjxb.so ABI version mismatch")
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str = "mjxb call"):
+    if rc != 0:
+        L = lib()
+        msg = L.mjxb_strerror(rc).decode()
+        if rc == -3:
+            msg += ": " + L.mjxb_last_cuda_error().decode()
+        raise MjxbError(f"{what} failed: {msg} ({rc})")

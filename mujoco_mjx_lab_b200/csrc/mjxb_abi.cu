@@ -1,0 +1,454 @@
+// mjxb_abi.cu -- the extern "C" boundary declared in include/mjxb.h (host side: model upload, launches, host-buffer arena).
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+
+#include "mjxb.h"
+#include "mjxb_device.cuh"
+
+using namespace mjxb;
+
+namespace {
+
+thread_local char g_cuda_err[512] = "";
+
+int cuda_fail(cudaError_t e, const char* what) {
+  snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", what, cudaGetErrorString(e));
+  return MJXB_ECUDA;
+}
+#define CU(call)                                         \
+  do {                                                   \
+    cudaError_t e_ = (call);                             \
+    if (e_ != cudaSuccess) return cuda_fail(e_, #call);  \
+  } while (0)
+
+struct Arena {  // device-resident env batch for the *_host entry points
+  int n = 0;
+  float *qpos = nullptr, *qvel = nullptr, *warm = nullptr, *time = nullptr, *aux = nullptr;
+  float *action = nullptr, *obs = nullptr, *reward = nullptr, *term = nullptr, *trunc = nullptr;
+  uint32_t* keys = nullptr;
+  cudaStream_t stream = nullptr;
+};
+
+}  // namespace
+
+struct mjxb_model {
+  DevModel host;
+  DevModel* dev = nullptr;
+  PairParam* dev_pp = nullptr;
+  int device = 0, num_sms = 0, warps = 0;
+  size_t smem = 0;
+  Arena arena;
+};
+
+namespace {
+
+void arena_free(Arena& a) {
+  float** ps[] = {&a.qpos, &a.qvel, &a.warm, &a.time, &a.aux, &a.action, &a.obs, &a.reward, &a.term, &a.trunc};
+  for (float** p : ps) { if (*p) cudaFree(*p); *p = nullptr; }
+  if (a.keys) cudaFree(a.keys);
+  a.keys = nullptr;
+  if (a.stream) cudaStreamDestroy(a.stream);
+  a.stream = nullptr;
+  a.n = 0;
+}
+
+int arena_ensure(mjxb_model* m, int n) {
+  Arena& a = m->arena;
+  if (a.n == n) return MJXB_OK;
+  arena_free(a);
+  const DevModel& C = m->host;
+  CU(cudaSetDevice(m->device));
+  CU(cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking));
+  size_t N = (size_t)n;
+  CU(cudaMalloc(&a.qpos, N * C.nq * 4)); CU(cudaMalloc(&a.qvel, N * C.nv * 4)); CU(cudaMalloc(&a.warm, N * C.nv * 4));
+  CU(cudaMalloc(&a.time, N * 4)); CU(cudaMalloc(&a.aux, N * MJXB_AUX_DIM * 4)); CU(cudaMalloc(&a.action, N * C.nu * 4));
+  CU(cudaMalloc(&a.obs, N * C.cfg.obs_dim * 4)); CU(cudaMalloc(&a.reward, N * 4)); CU(cudaMalloc(&a.term, N * 4));
+  CU(cudaMalloc(&a.trunc, N * 4)); CU(cudaMalloc(&a.keys, N * 8));
+  CU(cudaMemsetAsync(a.qpos, 0, N * C.nq * 4, a.stream)); CU(cudaMemsetAsync(a.qvel, 0, N * C.nv * 4, a.stream));
+  CU(cudaMemsetAsync(a.warm, 0, N * C.nv * 4, a.stream)); CU(cudaMemsetAsync(a.time, 0, N * 4, a.stream));
+  CU(cudaMemsetAsync(a.aux, 0, N * MJXB_AUX_DIM * 4, a.stream));
+  a.n = n;
+  return MJXB_OK;
+}
+
+int build_dev_model(const mjxb_model_blob& b, const mjxb_env_config* cfg, DevModel& D, PairParam* pp) {
+  memset(&D, 0, sizeof(D));
+  if (b.nv != NV) return MJXB_EUNSUPPORTED;  // the in-register factorisation is compiled for nv = 27 (humanoid family)
+  if (b.nbody > 32 || b.ngeom > 32 || b.nq > 32 || b.nlimit > 32 || b.ntlimit > 32 || b.nsensor > MJXB_MAXSENSOR) return MJXB_EUNSUPPORTED;
+  if (b.solver != 2 && b.solver != 1) return MJXB_EUNSUPPORTED;
+  if (b.solver == 1) return MJXB_EUNSUPPORTED;  // CG variant: next stage (train_apg.py:101-105)
+  D.nq = b.nq; D.nv = b.nv; D.nu = b.nu; D.nbody = b.nbody; D.njnt = b.njnt; D.ngeom = b.ngeom; D.nsite = b.nsite;
+  D.ntendon = b.ntendon; D.nsensor = b.nsensor; D.npair = b.npair; D.ncon = b.ncon; D.nefc = b.nefc; D.nlimit = b.nlimit;
+  D.ntlimit = b.ntlimit; D.ncon1 = b.ncon1; D.solver = b.solver; D.iterations = b.iterations; D.ls_iterations = b.ls_iterations;
+  D.damp_implicit = (b.integrator == 3) || (b.integrator == 0 && b.eulerdamp);
+  D.maxdepth = b.maxdepth;
+  D.timestep = b.timestep; D.tolerance = b.tolerance; D.ls_tolerance = b.ls_tolerance; D.meaninertia = b.meaninertia;
+  for (int k = 0; k < 3; k++) D.gravity[k] = b.gravity[k];
+  double tm = 0;
+  for (int i = 0; i < b.nbody; i++) {
+    D.body_parent[i] = b.body_parent[i]; D.body_depth[i] = b.body_depth[i]; D.body_subtree_end[i] = b.body_subtree_end[i];
+    D.body_jntadr[i] = b.body_jntadr[i]; D.body_jntnum[i] = b.body_jntnum[i];
+    for (int k = 0; k < 3; k++) { D.body_pos[i][k] = b.body_pos[i][k]; D.body_ipos[i][k] = b.body_ipos[i][k]; }
+    for (int k = 0; k < 4; k++) D.body_quat[i][k] = b.body_quat[i][k];
+    for (int k = 0; k < 6; k++) D.body_inertia[i][k] = b.body_inertia[i][k];
+    D.body_mass[i] = b.body_mass[i];
+    tm += b.body_mass[i];
+    if (i >= 1) {  // single kinematic tree rooted at body 1 (one subtree_com reference point)
+      int r = i;
+      while (b.body_parent[r] != 0) r = b.body_parent[r];
+      if (r != 1) return MJXB_EUNSUPPORTED;
+    }
+  }
+  D.total_mass = (float)tm;
+  for (int j = 0; j < b.njnt; j++) {
+    D.jnt_type[j] = b.jnt_type[j]; D.jnt_qposadr[j] = b.jnt_qposadr[j]; D.jnt_dofadr[j] = b.jnt_dofadr[j];
+    for (int k = 0; k < 3; k++) { D.jnt_pos[j][k] = b.jnt_pos[j][k]; D.jnt_axis[j][k] = b.jnt_axis[j][k]; }
+    if (b.jnt_type[j] != 0 && b.jnt_type[j] != 3) return MJXB_EUNSUPPORTED;
+  }
+  for (int i = 0; i < b.nlimit; i++) {
+    int j = b.lim_jnt[i];
+    D.lim_dof[i] = b.jnt_dofadr[j]; D.lim_qadr[i] = b.jnt_qposadr[j]; D.lim_row[i] = i;
+    D.lim_range[i][0] = b.jnt_range[j][0]; D.lim_range[i][1] = b.jnt_range[j][1];
+    D.lim_invweight[i] = b.dof_invweight0[b.jnt_dofadr[j]];
+    for (int k = 0; k < 2; k++) D.lim_solref[i][k] = b.jnt_solref[j][k];
+    for (int k = 0; k < 5; k++) D.lim_solimp[i][k] = b.jnt_solimp[j][k];
+  }
+  for (int d = 0; d < MJXB_MAXDOF; d++) { D.dof_act[d] = -1; D.dof_qadr[d] = -1; D.dof_parent[d] = -1; }
+  for (int d = 0; d < b.nv; d++) {
+    D.dof_body[d] = b.dof_body[d]; D.dof_jnt[d] = b.dof_jnt[d]; D.dof_parent[d] = b.dof_parent[d];
+    D.dof_armature[d] = b.dof_armature[d]; D.dof_damping[d] = b.dof_damping[d]; D.dof_stiffness[d] = b.dof_stiffness[d];
+    int j = b.dof_jnt[d];
+    if (b.jnt_type[j] == 3) D.dof_qadr[d] = b.jnt_qposadr[j];
+  }
+  for (int u = 0; u < b.nu; u++) {
+    int d = b.act_dof[u];
+    if (D.dof_act[d] >= 0) return MJXB_EUNSUPPORTED;  // one motor per dof
+    D.dof_act[d] = u; D.dof_gear[d] = b.act_gear[u];
+    D.dof_ctrl_lo[d] = b.act_ctrllimited[u] ? b.act_ctrlrange[u][0] : -3.0e38f;
+    D.dof_ctrl_hi[d] = b.act_ctrllimited[u] ? b.act_ctrlrange[u][1] : 3.0e38f;
+  }
+  for (int i = 0; i < b.nq; i++) { D.qpos0[i] = b.qpos0[i]; D.qpos_spring[i] = b.qpos_spring[i]; }
+  for (int j = 0; j < b.njnt; j++) {
+    int qa = b.jnt_qposadr[j], da = b.jnt_dofadr[j];
+    if (b.jnt_type[j] == 0) {
+      for (int k = 0; k < 3; k++) { D.qpos_kind[qa + k] = QK_FREEPOS; D.qpos_aux[qa + k] = da + k; }
+      for (int k = 0; k < 4; k++) { D.qpos_kind[qa + 3 + k] = QK_FREEQUAT; D.qpos_aux[qa + 3 + k] = (qa + 3) | (k << 8) | ((da + 3) << 16); }
+    } else {
+      D.qpos_kind[qa] = QK_HINGE; D.qpos_aux[qa] = da;
+    }
+  }
+  // dofs that move each body: walk the dof-parent chain from the body's (or nearest jointed ancestor's) last dof
+  for (int i = 1; i < b.nbody; i++) {
+    int bb = i;
+    while (bb > 0 && b.body_dofnum[bb] == 0) bb = b.body_parent[bb];
+    uint32_t mask = 0;
+    if (bb > 0)
+      for (int d = b.body_dofadr[bb] + b.body_dofnum[bb] - 1; d >= 0; d = b.dof_parent[d]) mask |= 1u << d;
+    D.body_dofmask[i] = mask;
+  }
+  for (int g = 0; g < b.ngeom; g++) {
+    D.geom_body[g] = b.geom_body[g];
+    for (int k = 0; k < 3; k++) D.geom_pos[g][k] = b.geom_pos[g][k];
+    // local z axis of the geom frame (third column of the rotation of geom_quat), in double
+    double w = b.geom_quat[g][0], x = b.geom_quat[g][1], y = b.geom_quat[g][2], z = b.geom_quat[g][3];
+    D.geom_axis[g][0] = (float)(2 * (x * z + w * y)); D.geom_axis[g][1] = (float)(2 * (y * z - w * x));
+    D.geom_axis[g][2] = (float)(w * w - x * x - y * y + z * z);
+    D.geom_rad[g] = b.geom_size[g][0]; D.geom_half[g] = b.geom_size[g][1];
+    if (b.geom_type[g] == 0) { D.geom_rad[g] = 0.0f; D.geom_half[g] = 0.0f; }
+  }
+  if (b.npair > MJXB_MAXPAIR || b.ncon > 0xffff || b.nefc > 0xffff) return MJXB_EUNSUPPORTED;
+  for (int p = 0; p < b.npair; p++) {
+    D.pair_w0[p] = (uint32_t)b.pair_g1[p] | ((uint32_t)b.pair_g2[p] << 8) | ((uint32_t)b.pair_kind[p] << 16) | ((uint32_t)b.pair_condim[p] << 24);
+    D.pair_w1[p] = (uint32_t)b.pair_conadr[p] | ((uint32_t)b.pair_efcadr[p] << 16);
+    pp[p].mu = b.pair_mu[p]; pp[p].invweight = b.pair_invweight[p];
+    for (int k = 0; k < 2; k++) pp[p].solref[k] = b.pair_solref[p][k];
+    for (int k = 0; k < 5; k++) pp[p].solimp[k] = b.pair_solimp[p][k];
+    if (b.pair_condim[p] != 1 && b.pair_condim[p] != 3) return MJXB_EUNSUPPORTED;
+  }
+  for (int i = 0; i < b.ntlimit; i++) {
+    int t = b.lim_ten[i];
+    D.ten_nwrap[i] = b.ten_nwrap[t]; D.ten_row[i] = b.nlimit + i;
+    for (int w = 0; w < MJXB_MAXWRAP; w++) { D.ten_dof[i][w] = b.ten_dof[t][w]; D.ten_qpos[i][w] = b.ten_qpos[t][w]; D.ten_coef[i][w] = b.ten_coef[t][w]; }
+    for (int k = 0; k < 2; k++) { D.ten_range[i][k] = b.ten_range[t][k]; D.ten_solref[i][k] = b.ten_solref[t][k]; }
+    for (int k = 0; k < 5; k++) D.ten_solimp[i][k] = b.ten_solimp[t][k];
+    D.ten_invweight[i] = b.ten_invweight0[t];
+  }
+  for (int s = 0; s < b.nsite; s++) {
+    D.site_body[s] = b.site_body[s];
+    for (int k = 0; k < 3; k++) { D.site_pos[s][k] = b.site_pos[s][k]; D.site_size[s][k] = b.site_size[s][k]; }
+    for (int k = 0; k < 4; k++) D.site_quat[s][k] = b.site_quat[s][k];
+  }
+  for (int s = 0; s < b.nsensor; s++) D.sensor_site[s] = b.sensor_site[s];
+  if (cfg) {
+    D.cfg = *cfg;
+    if (cfg->obs_dim != 1 + 3 + (b.nq - 7) + b.nv + 2 || cfg->obs_dim > MJXB_MAXOBS) return MJXB_EINVAL;
+    if (cfg->pelvis_body_id < 0 || cfg->pelvis_body_id >= b.nbody || cfg->head_body_id < 0 || cfg->head_body_id >= b.nbody) return MJXB_EINVAL;
+    if (cfg->touch_sensor_right_id < 0 || cfg->touch_sensor_right_id >= b.nsensor || cfg->touch_sensor_left_id < 0 ||
+        cfg->touch_sensor_left_id >= b.nsensor) return MJXB_EINVAL;
+    for (int i = 0; i < b.nu; i++) if (cfg->act_perm[i] < 0 || cfg->act_perm[i] >= b.nu) return MJXB_EINVAL;
+    for (int i = 0; i < cfg->obs_dim; i++) if (cfg->obs_perm[i] < 0 || cfg->obs_perm[i] >= cfg->obs_dim) return MJXB_EINVAL;
+  } else {
+    D.cfg.obs_dim = 1 + 3 + (b.nq - 7) + b.nv + 2;
+    D.cfg.pelvis_body_id = 0; D.cfg.head_body_id = 0;
+  }
+  return MJXB_OK;
+}
+
+int launch(const mjxb_model* m, const StepArgs& args, bool dbg, cudaStream_t stream) {
+  int cur = 0;
+  CU(cudaGetDevice(&cur));
+  if (cur != m->device) CU(cudaSetDevice(m->device));
+  const int warps = m->warps;
+  int grid = (args.n_env + warps - 1) / warps;
+  if (grid > m->num_sms) grid = m->num_sms;
+  if (dbg) mjxb_step_kernel<true><<<grid, warps * 32, m->smem, stream>>>(m->dev, m->dev_pp, args);
+  else mjxb_step_kernel<false><<<grid, warps * 32, m->smem, stream>>>(m->dev, m->dev_pp, args);
+  cudaError_t e = cudaGetLastError();
+  if (cur != m->device) cudaSetDevice(cur);
+  if (e != cudaSuccess) return cuda_fail(e, "mjxb_step_kernel launch");
+  return MJXB_OK;
+}
+
+bool state_ok(const mjxb_state& s, bool need_aux) {
+  return s.qpos && s.qvel && s.qacc_warmstart && s.time && (!need_aux || s.aux);
+}
+
+}  // namespace
+
+extern "C" {
+
+int mjxb_abi_version(void) { return MJXB_ABI_VERSION; }
+size_t mjxb_blob_sizeof(void) { return sizeof(mjxb_model_blob); }
+size_t mjxb_env_config_sizeof(void) { return sizeof(mjxb_env_config); }
+const char* mjxb_last_cuda_error(void) { return g_cuda_err; }
+const char* mjxb_strerror(int code) {
+  switch (code) {
+    case MJXB_OK: return "ok";
+    case MJXB_EINVAL: return "invalid argument";
+    case MJXB_EBLOB: return "bad model blob (magic/version/size)";
+    case MJXB_ECUDA: return "CUDA error (see mjxb_last_cuda_error)";
+    case MJXB_ENOGPU: return "no CUDA device (there is no CPU fallback)";
+    case MJXB_EUNSUPPORTED: return "model outside the compiled humanoid family (nv=27, hinge/free joints, Newton, pyramidal)";
+    default: return "unknown error";
+  }
+}
+
+int mjxb_model_create(const void* blob, size_t blob_bytes, const mjxb_env_config* cfg, int device, mjxb_model** out) {
+  if (!blob || !out) return MJXB_EINVAL;
+  *out = nullptr;
+  if (blob_bytes != sizeof(mjxb_model_blob)) return MJXB_EBLOB;
+  const mjxb_model_blob& b = *reinterpret_cast<const mjxb_model_blob*>(blob);
+  if (b.magic != MJXB_BLOB_MAGIC || b.version != MJXB_BLOB_VERSION) return MJXB_EBLOB;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return MJXB_ENOGPU; }
+  if (device < 0 || device >= ndev) return MJXB_EINVAL;
+  mjxb_model* m = new (std::nothrow) mjxb_model();
+  if (!m) return MJXB_EINVAL;
+  static PairParam pp[MJXB_MAXPAIR];
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  memset(pp, 0, sizeof(pp));
+  int rc = build_dev_model(b, cfg, m->host, pp);
+  if (rc != MJXB_OK) { delete m; return rc; }
+  m->device = device;
+  cudaError_t e;
+#define CUX(call) if ((e = (call)) != cudaSuccess) { cuda_fail(e, #call); mjxb_model_destroy(m); return MJXB_ECUDA; }
+  int cur = 0;
+  CUX(cudaGetDevice(&cur));
+  CUX(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUX(cudaGetDeviceProperties(&prop, device));
+  m->num_sms = prop.multiProcessorCount;
+  const size_t model_bytes = (sizeof(DevModel) + 15) & ~size_t(15);
+  const size_t avail = prop.sharedMemPerBlockOptin;
+  int warps = (int)((avail - model_bytes) / sizeof(WarpS));
+  if (warps > MAX_WARPS) warps = MAX_WARPS;
+  if (warps < 1) { delete m; cudaSetDevice(cur); return MJXB_EUNSUPPORTED; }
+  m->warps = warps;
+  m->smem = model_bytes + (size_t)warps * sizeof(WarpS);
+  CUX(cudaFuncSetAttribute(mjxb_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem));
+  CUX(cudaFuncSetAttribute(mjxb_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem));
+  CUX(cudaMalloc(&m->dev, sizeof(DevModel)));
+  CUX(cudaMalloc(&m->dev_pp, sizeof(pp)));
+  CUX(cudaMemcpy(m->dev, &m->host, sizeof(DevModel), cudaMemcpyHostToDevice));
+  CUX(cudaMemcpy(m->dev_pp, pp, sizeof(pp), cudaMemcpyHostToDevice));
+  cudaSetDevice(cur);
+#undef CUX
+  *out = m;
+  return MJXB_OK;
+}
+
+void mjxb_model_destroy(mjxb_model* m) {
+  if (!m) return;
+  arena_free(m->arena);
+  if (m->dev) cudaFree(m->dev);
+  if (m->dev_pp) cudaFree(m->dev_pp);
+  delete m;
+}
+
+int mjxb_model_dims(const mjxb_model* m, int32_t dims[8]) {
+  if (!m || !dims) return MJXB_EINVAL;
+  const DevModel& C = m->host;
+  dims[0] = C.nq; dims[1] = C.nv; dims[2] = C.nu; dims[3] = C.nbody; dims[4] = C.ncon; dims[5] = C.nefc; dims[6] = C.nsensor;
+  dims[7] = C.cfg.obs_dim;
+  return MJXB_OK;
+}
+
+size_t mjxb_model_scratch_bytes(const mjxb_model* m) { (void)m; return 0; }
+
+int mjxb_launch_config(const mjxb_model* m, int32_t cfg[4]) {  // warps per CTA, dynamic smem bytes, SM count, sizeof(WarpS)
+  if (!m || !cfg) return MJXB_EINVAL;
+  cfg[0] = m->warps; cfg[1] = (int32_t)m->smem; cfg[2] = m->num_sms; cfg[3] = (int32_t)sizeof(WarpS);
+  return MJXB_OK;
+}
+
+int mjxb_reset(const mjxb_model* m, int32_t n_env, const uint32_t* keys, mjxb_state out, float* obs, int32_t* status, void* stream) {
+  if (!m || n_env <= 0 || !keys || !obs || !state_ok(out, true)) return MJXB_EINVAL;
+  StepArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n_env = n_env; a.mode = MODE_ENV_RESET; a.nsteps = 1; a.out = out; a.in = out; a.keys = keys; a.obs = obs; a.status = status;
+  return launch(m, a, false, (cudaStream_t)stream);
+}
+
+int mjxb_step(const mjxb_model* m, int32_t n_env, mjxb_state in, const float* action, mjxb_state out, float* obs, float* reward,
+              float* terminated, float* truncated, int32_t* status, void* stream) {
+  if (!m || n_env <= 0 || !action || !obs || !reward || !terminated || !truncated || !state_ok(in, true) || !state_ok(out, true))
+    return MJXB_EINVAL;
+  StepArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n_env = n_env; a.mode = MODE_ENV_STEP; a.nsteps = 1; a.in = in; a.out = out; a.action = action; a.obs = obs; a.reward = reward;
+  a.terminated = terminated; a.truncated = truncated; a.status = status;
+  return launch(m, a, false, (cudaStream_t)stream);
+}
+
+int mjxb_step_autoreset(const mjxb_model* m, int32_t n_env, mjxb_state in, const float* action, const uint32_t* keys, mjxb_state out,
+                        float* obs, float* reward, float* terminated, float* truncated, uint8_t* reset_mask, int32_t* status,
+                        void* stream) {
+  if (!m || n_env <= 0 || !action || !keys || !obs || !reward || !terminated || !truncated || !state_ok(in, true) || !state_ok(out, true))
+    return MJXB_EINVAL;
+  StepArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n_env = n_env; a.mode = MODE_ENV_STEP; a.nsteps = 1; a.autoreset = 1; a.in = in; a.out = out; a.action = action; a.keys = keys;
+  a.obs = obs; a.reward = reward; a.terminated = terminated; a.truncated = truncated; a.reset_mask = reset_mask; a.status = status;
+  return launch(m, a, false, (cudaStream_t)stream);
+}
+
+int mjxb_physics_step(const mjxb_model* m, int32_t n_env, mjxb_state io, const float* ctrl, int32_t nsteps, const mjxb_debug* dbg,
+                      int32_t* status, void* stream) {
+  if (!m || n_env <= 0 || nsteps <= 0 || !state_ok(io, false)) return MJXB_EINVAL;
+  StepArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n_env = n_env; a.mode = MODE_PHYS_STEP; a.nsteps = nsteps; a.in = io; a.out = io; a.action = ctrl; a.status = status;
+  if (dbg) a.dbg = *dbg;
+  return launch(m, a, dbg != nullptr, (cudaStream_t)stream);
+}
+
+int mjxb_forward(const mjxb_model* m, int32_t n_env, mjxb_state io, const float* ctrl, const mjxb_debug* dbg, int32_t* status,
+                 void* stream) {
+  if (!m || n_env <= 0 || !state_ok(io, false)) return MJXB_EINVAL;
+  StepArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n_env = n_env; a.mode = MODE_FORWARD; a.nsteps = 1; a.in = io; a.out = io; a.action = ctrl; a.status = status;
+  if (dbg) a.dbg = *dbg;
+  return launch(m, a, dbg != nullptr, (cudaStream_t)stream);
+}
+
+int mjxb_speed_test(const mjxb_model* m, int32_t n_env, const float* vel, float* pos, int32_t iters, void* stream) {
+  if (!m || n_env <= 0 || !vel || !pos || iters <= 0) return MJXB_EINVAL;
+  StepArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n_env = n_env; a.mode = MODE_SPEED_TEST; a.nsteps = iters; a.vel = vel; a.pos = pos;
+  return launch(m, a, false, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------- host-buffer variants (the end-to-end path)
+static mjxb_state arena_state(const Arena& a) {
+  mjxb_state s;
+  s.qpos = a.qpos; s.qvel = a.qvel; s.qacc_warmstart = a.warm; s.time = a.time; s.aux = a.aux;
+  return s;
+}
+
+int mjxb_reset_host(mjxb_model* m, int32_t n_env, const uint32_t* keys_host, float* obs_host) {
+  if (!m || n_env <= 0 || !keys_host || !obs_host) return MJXB_EINVAL;
+  int rc = arena_ensure(m, n_env);
+  if (rc) return rc;
+  Arena& a = m->arena;
+  size_t N = (size_t)n_env;
+  CU(cudaMemcpyAsync(a.keys, keys_host, N * 8, cudaMemcpyHostToDevice, a.stream));
+  rc = mjxb_reset(m, n_env, a.keys, arena_state(a), a.obs, nullptr, a.stream);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(obs_host, a.obs, N * m->host.cfg.obs_dim * 4, cudaMemcpyDeviceToHost, a.stream));
+  CU(cudaStreamSynchronize(a.stream));
+  return MJXB_OK;
+}
+
+static int step_host_impl(mjxb_model* m, int32_t n_env, const float* action_host, const uint32_t* keys_host, float* obs_host,
+                          float* reward_host, float* terminated_host, float* truncated_host) {
+  if (!m || n_env <= 0 || !action_host || !obs_host || !reward_host || !terminated_host || !truncated_host) return MJXB_EINVAL;
+  Arena& a = m->arena;
+  if (a.n != n_env) return MJXB_EINVAL;  // reset_host / state_set_host must have created the batch
+  size_t N = (size_t)n_env;
+  CU(cudaMemcpyAsync(a.action, action_host, N * m->host.nu * 4, cudaMemcpyHostToDevice, a.stream));
+  int rc;
+  if (keys_host) {
+    CU(cudaMemcpyAsync(a.keys, keys_host, N * 8, cudaMemcpyHostToDevice, a.stream));
+    rc = mjxb_step_autoreset(m, n_env, arena_state(a), a.action, a.keys, arena_state(a), a.obs, a.reward, a.term, a.trunc, nullptr,
+                             nullptr, a.stream);
+  } else {
+    rc = mjxb_step(m, n_env, arena_state(a), a.action, arena_state(a), a.obs, a.reward, a.term, a.trunc, nullptr, a.stream);
+  }
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(obs_host, a.obs, N * m->host.cfg.obs_dim * 4, cudaMemcpyDeviceToHost, a.stream));
+  CU(cudaMemcpyAsync(reward_host, a.reward, N * 4, cudaMemcpyDeviceToHost, a.stream));
+  CU(cudaMemcpyAsync(terminated_host, a.term, N * 4, cudaMemcpyDeviceToHost, a.stream));
+  CU(cudaMemcpyAsync(truncated_host, a.trunc, N * 4, cudaMemcpyDeviceToHost, a.stream));
+  CU(cudaStreamSynchronize(a.stream));
+  return MJXB_OK;
+}
+
+int mjxb_step_host(mjxb_model* m, int32_t n_env, const float* action_host, float* obs_host, float* reward_host, float* terminated_host,
+                   float* truncated_host) {
+  return step_host_impl(m, n_env, action_host, nullptr, obs_host, reward_host, terminated_host, truncated_host);
+}
+
+int mjxb_step_autoreset_host(mjxb_model* m, int32_t n_env, const float* action_host, const uint32_t* keys_host, float* obs_host,
+                             float* reward_host, float* terminated_host, float* truncated_host) {
+  if (!keys_host) return MJXB_EINVAL;
+  return step_host_impl(m, n_env, action_host, keys_host, obs_host, reward_host, terminated_host, truncated_host);
+}
+
+int mjxb_state_get_host(mjxb_model* m, int32_t n_env, float* qpos, float* qvel, float* qacc_warmstart, float* time, float* aux) {
+  if (!m || n_env <= 0 || m->arena.n != n_env) return MJXB_EINVAL;
+  Arena& a = m->arena;
+  size_t N = (size_t)n_env;
+  if (qpos) CU(cudaMemcpyAsync(qpos, a.qpos, N * m->host.nq * 4, cudaMemcpyDeviceToHost, a.stream));
+  if (qvel) CU(cudaMemcpyAsync(qvel, a.qvel, N * m->host.nv * 4, cudaMemcpyDeviceToHost, a.stream));
+  if (qacc_warmstart) CU(cudaMemcpyAsync(qacc_warmstart, a.warm, N * m->host.nv * 4, cudaMemcpyDeviceToHost, a.stream));
+  if (time) CU(cudaMemcpyAsync(time, a.time, N * 4, cudaMemcpyDeviceToHost, a.stream));
+  if (aux) CU(cudaMemcpyAsync(aux, a.aux, N * MJXB_AUX_DIM * 4, cudaMemcpyDeviceToHost, a.stream));
+  CU(cudaStreamSynchronize(a.stream));
+  return MJXB_OK;
+}
+
+int mjxb_state_set_host(mjxb_model* m, int32_t n_env, const float* qpos, const float* qvel, const float* qacc_warmstart,
+                        const float* time, const float* aux) {
+  if (!m || n_env <= 0) return MJXB_EINVAL;
+  int rc = arena_ensure(m, n_env);
+  if (rc) return rc;
+  Arena& a = m->arena;
+  size_t N = (size_t)n_env;
+  if (qpos) CU(cudaMemcpyAsync(a.qpos, qpos, N * m->host.nq * 4, cudaMemcpyHostToDevice, a.stream));
+  if (qvel) CU(cudaMemcpyAsync(a.qvel, qvel, N * m->host.nv * 4, cudaMemcpyHostToDevice, a.stream));
+  if (qacc_warmstart) CU(cudaMemcpyAsync(a.warm, qacc_warmstart, N * m->host.nv * 4, cudaMemcpyHostToDevice, a.stream));
+  if (time) CU(cudaMemcpyAsync(a.time, time, N * 4, cudaMemcpyHostToDevice, a.stream));
+  if (aux) CU(cudaMemcpyAsync(a.aux, aux, N * MJXB_AUX_DIM * 4, cudaMemcpyHostToDevice, a.stream));
+  CU(cudaStreamSynchronize(a.stream));
+  return MJXB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,1410 @@
+// mjxb_device.cuh -- the fused batched humanoid step for sm_100a: one warp per environment.
+//
+// Replaces the vmapped mjx.step / mjx.forward + env glue of reference src/envs.py:108-202,333-495 and
+// mjx_humanoid_speed_test.py:48-57 (stage list: SURVEY.md Appendix B).  Design:
+//   * lane <-> dof / body / geom pair / constraint row; no __syncthreads after the prologue, only __syncwarp;
+//   * model constants staged once per CTA in shared memory; per-env working set ~13 KB of shared memory;
+//   * only CANDIDATE constraint rows (pos < 0) are ever materialised (MJX keeps all 187, zero-masked);
+//   * the Newton Hessian row of dof i lives in lane i's registers: assembled from 128-bit broadcast loads of the
+//     Jacobian rows, factorised in registers (Cholesky, column broadcast through a 2x32-float smem buffer),
+//     forward-substituted in registers; one code instance serves M, H and (M + h*damping);
+//   * per-env early exit from the Newton and line-search loops (a vmapped while_loop cannot).
+// FP32 CUDA cores only: nv = 27 contractions with data-dependent masks are not tensor-core shaped.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mjxb.h"
+
+namespace mjxb {
+
+constexpr int NV = 27;    // compile-time dof count: the register-resident factorisation is statically unrolled
+constexpr int NVP = 28;   // row stride (floats) of M and J: 16-byte aligned rows for 128-bit loads
+constexpr int CAP = 48;   // candidate constraint rows kept in shared memory per env
+constexpr int NSTRIP = (CAP + 31) / 32;
+constexpr int MAXCC = 24; // candidate contacts per env
+constexpr int MAX_WARPS = 12;  // warps (= envs in flight) per CTA; one CTA per SM, bounded by shared memory
+constexpr unsigned FULL = 0xffffffffu;
+constexpr float MINVAL = 1e-15f;
+
+enum { MODE_ENV_STEP = 0, MODE_ENV_RESET = 1, MODE_PHYS_STEP = 2, MODE_FORWARD = 3, MODE_SPEED_TEST = 4 };
+enum { PAIR_PLANE_SPHERE = 0, PAIR_PLANE_CAPSULE = 1, PAIR_SPHERE_SPHERE = 2, PAIR_SPHERE_CAPSULE = 3, PAIR_CAPSULE_CAPSULE = 4 };
+enum { ROW_LIMIT = 0, ROW_TENDON = 1, ROW_CON1 = 2, ROW_CON3 = 3 };
+enum { QK_HINGE = 0, QK_FREEPOS = 1, QK_FREEQUAT = 2 };
+
+struct PairParam { float mu, invweight, solref[2], solimp[5]; };
+
+// Device copy of the model: the fields of mjxb_model_blob the kernels need, plus derived tables.
+struct DevModel {
+  int nq, nv, nu, nbody, njnt, ngeom, nsite, ntendon, nsensor, npair, ncon, nefc, nlimit, ntlimit, ncon1;
+  int solver, iterations, ls_iterations, damp_implicit, maxdepth;
+  float timestep, gravity[3], tolerance, ls_tolerance, meaninertia, total_mass;
+  int body_parent[MJXB_MAXBODY], body_depth[MJXB_MAXBODY], body_subtree_end[MJXB_MAXBODY], body_jntadr[MJXB_MAXBODY],
+      body_jntnum[MJXB_MAXBODY];
+  uint32_t body_dofmask[MJXB_MAXBODY];  // dofs that move the body (ancestors-or-self)
+  float body_pos[MJXB_MAXBODY][3], body_quat[MJXB_MAXBODY][4], body_ipos[MJXB_MAXBODY][3], body_inertia[MJXB_MAXBODY][6],
+      body_mass[MJXB_MAXBODY];
+  int jnt_type[MJXB_MAXJNT], jnt_qposadr[MJXB_MAXJNT], jnt_dofadr[MJXB_MAXJNT];
+  float jnt_pos[MJXB_MAXJNT][3], jnt_axis[MJXB_MAXJNT][3];
+  int lim_dof[MJXB_MAXJNT], lim_qadr[MJXB_MAXJNT], lim_row[MJXB_MAXJNT];
+  float lim_range[MJXB_MAXJNT][2], lim_invweight[MJXB_MAXJNT], lim_solref[MJXB_MAXJNT][2], lim_solimp[MJXB_MAXJNT][5];
+  int dof_body[MJXB_MAXDOF], dof_jnt[MJXB_MAXDOF], dof_parent[MJXB_MAXDOF], dof_qadr[MJXB_MAXDOF], dof_act[MJXB_MAXDOF];
+  float dof_armature[MJXB_MAXDOF], dof_damping[MJXB_MAXDOF], dof_stiffness[MJXB_MAXDOF], dof_gear[MJXB_MAXDOF],
+      dof_ctrl_lo[MJXB_MAXDOF], dof_ctrl_hi[MJXB_MAXDOF];
+  int qpos_kind[MJXB_MAXQ], qpos_aux[MJXB_MAXQ];  // integrator addressing: hinge -> dof; free pos -> dof; free quat -> (qadr | comp<<8 | dof<<16)
+  float qpos0[MJXB_MAXQ], qpos_spring[MJXB_MAXQ];
+  int geom_body[MJXB_MAXGEOM];
+  float geom_pos[MJXB_MAXGEOM][3], geom_axis[MJXB_MAXGEOM][3], geom_rad[MJXB_MAXGEOM], geom_half[MJXB_MAXGEOM];
+  uint32_t pair_w0[MJXB_MAXPAIR];  // g1 | g2<<8 | kind<<16 | condim<<24
+  uint32_t pair_w1[MJXB_MAXPAIR];  // conadr | efcadr<<16
+  int ten_nwrap[MJXB_MAXTENDON], ten_dof[MJXB_MAXTENDON][MJXB_MAXWRAP], ten_qpos[MJXB_MAXTENDON][MJXB_MAXWRAP], ten_row[MJXB_MAXTENDON];
+  float ten_coef[MJXB_MAXTENDON][MJXB_MAXWRAP], ten_range[MJXB_MAXTENDON][2], ten_solref[MJXB_MAXTENDON][2],
+      ten_solimp[MJXB_MAXTENDON][5], ten_invweight[MJXB_MAXTENDON];
+  int site_body[MJXB_MAXSITE], sensor_site[MJXB_MAXSENSOR];
+  float site_pos[MJXB_MAXSITE][3], site_quat[MJXB_MAXSITE][4], site_size[MJXB_MAXSITE][3];
+  mjxb_env_config cfg;
+  int pad_[2];
+};
+
+struct StepArgs {
+  int n_env, mode, nsteps, autoreset;
+  mjxb_state in, out;
+  const float* action;   // [n, nu] (env modes: raw policy action; physics modes: ctrl) or NULL
+  const uint32_t* keys;  // [n, 2]
+  float *obs, *reward, *terminated, *truncated;
+  uint8_t* reset_mask;
+  int32_t* status;
+  const float* vel;      // speed test
+  float* pos;
+  mjxb_debug dbg;
+};
+
+// shared-memory vector slots (32 floats each)
+enum { VQPOS = 0, VQVEL, VCTRL, VX, VY, VTMP, NVEC };
+
+struct __align__(16) WarpS {
+  alignas(16) float M[NV * NVP];
+  union {
+    float L[NV * NV];  // Cholesky factor rows for the backward substitution
+    struct {
+      float xpos[MJXB_MAXBODY][3];
+      float xquat[MJXB_MAXBODY][4];
+      float cinert[MJXB_MAXBODY][10];  // later: composite inertia, in place
+      float cvel[MJXB_MAXBODY][6];     // later: subtree-summed cfrc
+      float cacc[MJXB_MAXBODY][6];     // later: body-local cfrc
+    } a;
+  };
+  alignas(16) float J[CAP * NVP];
+  float cdof[NV + 1][6];
+  alignas(16) float vec[NVEC][32];
+  alignas(16) float col[2][32];
+  float rD[CAP], raref[CAP], rJaref[CAP], rjv[CAP], rforce[CAP];
+  int rinfo[CAP];
+  float gpos[MJXB_MAXGEOM][3], gaxis[MJXB_MAXGEOM][3];
+  float cc_n[MAXCC][3], cc_t1[MAXCC][3], cc_t2[MAXCC][3], cc_pos[MAXCC][3], cc_dist[MAXCC];
+  int cc_pair[MAXCC], cc_row[MAXCC];
+  float site_xpos[MJXB_MAXSITE][3], site_xmat[MJXB_MAXSITE][9];
+  float pelvis_pos[3], pelvis_quat[4], head_pos[3];
+  float pad_[2];
+};
+
+// ------------------------------------------------------------------------------------------- small math
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+__device__ __forceinline__ float dot3(const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+__device__ __forceinline__ void cross3(float* r, const float* a, const float* b) {
+  float x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+// x / (|x| + 1e-6*(|x|==0)), returns |x|   (mjx math.normalize_with_norm)
+__device__ __forceinline__ float normalize3(float* a) {
+  float n = sqrtf(dot3(a, a));
+  float inv = 1.0f / (n + (n == 0.0f ? 1e-6f : 0.0f));
+  a[0] *= inv; a[1] *= inv; a[2] *= inv;
+  return n;
+}
+__device__ __forceinline__ void quat_mul(float* r, const float* a, const float* b) {
+  float w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+  float x = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+  float y = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+  float z = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+  r[0] = w; r[1] = x; r[2] = y; r[3] = z;
+}
+__device__ __forceinline__ void rotq(float* r, const float* v, const float* q) {  // mjx math.rotate
+  float s = q[0];
+  const float* u = q + 1;
+  float uv = dot3(u, v), uu = dot3(u, u), c[3];
+  cross3(c, u, v);
+#pragma unroll
+  for (int k = 0; k < 3; k++) r[k] = 2.0f * (uv * u[k]) + (s * s - uu) * v[k] + 2.0f * s * c[k];
+}
+__device__ __forceinline__ void quat_to_mat(float* m, const float* q) {
+  float w = q[0], x = q[1], y = q[2], z = q[3];
+  m[0] = w * w + x * x - y * y - z * z; m[1] = 2.0f * (x * y - w * z); m[2] = 2.0f * (x * z + w * y);
+  m[3] = 2.0f * (x * y + w * z); m[4] = w * w - x * x + y * y - z * z; m[5] = 2.0f * (y * z - w * x);
+  m[6] = 2.0f * (x * z - w * y); m[7] = 2.0f * (y * z + w * x); m[8] = w * w - x * x - y * y + z * z;
+}
+__device__ __forceinline__ void inert_mul(float* r, const float* i, const float* v) {
+  float c1[3], c2[3];
+  cross3(c1, i + 6, v + 3);
+  cross3(c2, i + 6, v);
+  r[0] = i[0] * v[0] + i[3] * v[1] + i[4] * v[2] + c1[0];
+  r[1] = i[3] * v[0] + i[1] * v[1] + i[5] * v[2] + c1[1];
+  r[2] = i[4] * v[0] + i[5] * v[1] + i[2] * v[2] + c1[2];
+  r[3] = i[9] * v[3] - c2[0]; r[4] = i[9] * v[4] - c2[1]; r[5] = i[9] * v[5] - c2[2];
+}
+__device__ __forceinline__ void motion_cross(float* r, const float* u, const float* v) {
+  float a[3], b[3], c[3];
+  cross3(a, u, v); cross3(b, u, v + 3); cross3(c, u + 3, v);
+#pragma unroll
+  for (int k = 0; k < 3; k++) { r[k] = a[k]; r[3 + k] = b[k] + c[k]; }
+}
+__device__ __forceinline__ void motion_cross_force(float* r, const float* v, const float* f) {
+  float a[3], b[3], c[3];
+  cross3(a, v, f); cross3(b, v + 3, f + 3); cross3(c, v, f + 3);
+#pragma unroll
+  for (int k = 0; k < 3; k++) { r[k] = a[k] + b[k]; r[3 + k] = c[k]; }
+}
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+
+// ------------------------------------------------------------------------------------------- threefry / jax.random
+__device__ __forceinline__ uint32_t rotl32(uint32_t v, int r) { return (v << r) | (v >> (32 - r)); }
+__device__ __forceinline__ void threefry2x32(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t& o0, uint32_t& o1) {
+  uint32_t ks0 = k0, ks1 = k1, ks2 = k0 ^ k1 ^ 0x1BD11BDAu;
+  uint32_t x0 = c0 + ks0, x1 = c1 + ks1;
+#define MJXB_TF_R(r) { x0 += x1; x1 = rotl32(x1, r); x1 ^= x0; }
+  MJXB_TF_R(13) MJXB_TF_R(15) MJXB_TF_R(26) MJXB_TF_R(6)  x0 += ks1; x1 += ks2 + 1u;
+  MJXB_TF_R(17) MJXB_TF_R(29) MJXB_TF_R(16) MJXB_TF_R(24) x0 += ks2; x1 += ks0 + 2u;
+  MJXB_TF_R(13) MJXB_TF_R(15) MJXB_TF_R(26) MJXB_TF_R(6)  x0 += ks0; x1 += ks1 + 3u;
+  MJXB_TF_R(17) MJXB_TF_R(29) MJXB_TF_R(16) MJXB_TF_R(24) x0 += ks1; x1 += ks2 + 4u;
+  MJXB_TF_R(13) MJXB_TF_R(15) MJXB_TF_R(26) MJXB_TF_R(6)  x0 += ks2; x1 += ks0 + 5u;
+#undef MJXB_TF_R
+  o0 = x0; o1 = x1;
+}
+// jax.random.uniform(key, (n,), f32, minval, maxval)[i] with threefry_partitionable
+__device__ __forceinline__ float jax_uniform(uint32_t k0, uint32_t k1, uint32_t i, float minval, float maxval) {
+  uint32_t a, b;
+  threefry2x32(k0, k1, 0u, i, a, b);
+  float f = __uint_as_float(((a ^ b) >> 9) | 0x3F800000u) - 1.0f;
+  return fmaxf(minval, __fadd_rn(__fmul_rn(f, maxval - minval), minval));
+}
+
+// ------------------------------------------------------------------------------------------- constraint impedance (mjx constraint._kbi)
+__device__ __forceinline__ void kbi(float timestep, const float* solref, const float* solimp, float pos, float& k, float& b, float& imp) {
+  float timeconst = fmaxf(solref[0], 2.0f * timestep), dampratio = solref[1];
+  float dmin = clampf(solimp[0], 1e-4f, 0.9999f), dmax = clampf(solimp[1], 1e-4f, 0.9999f);
+  float width = fmaxf(MINVAL, solimp[2]), mid = clampf(solimp[3], 1e-4f, 0.9999f), power = fmaxf(1.0f, solimp[4]);
+  k = 1.0f / (dmax * dmax * timeconst * timeconst * dampratio * dampratio);
+  b = 2.0f / (dmax * timeconst);
+  if (solref[0] <= 0.0f) k = -solref[0] / (dmax * dmax);
+  if (solref[1] <= 0.0f) b = -solref[1] / dmax;
+  float x = fabsf(pos) / width;
+  float ia, ib;
+  if (power == 2.0f) { ia = (1.0f / mid) * (x * x); ib = 1.0f - (1.0f / (1.0f - mid)) * ((1.0f - x) * (1.0f - x)); }
+  else if (power == 1.0f) { ia = x; ib = x; }
+  else { ia = (1.0f / powf(mid, power - 1.0f)) * powf(x, power); ib = 1.0f - (1.0f / powf(1.0f - mid, power - 1.0f)) * powf(1.0f - x, power); }
+  float y = x < mid ? ia : ib;
+  imp = clampf(dmin + y * (dmax - dmin), dmin, dmax);
+  if (x > 1.0f) imp = dmax;
+}
+
+// ------------------------------------------------------------------------------------------- collision primitives (mjx collision_primitive / math)
+__device__ __forceinline__ void sphere_sphere(float& dist, float* pos, float* n, const float* p1, float r1, const float* p2, float r2) {
+  n[0] = p2[0] - p1[0]; n[1] = p2[1] - p1[1]; n[2] = p2[2] - p1[2];
+  float len = normalize3(n);
+  if (len == 0.0f) { n[0] = 1.0f; n[1] = 0.0f; n[2] = 0.0f; }
+  dist = len - (r1 + r2);
+  float s = r1 + dist * 0.5f;
+  pos[0] = p1[0] + n[0] * s; pos[1] = p1[1] + n[1] * s; pos[2] = p1[2] + n[2] * s;
+}
+__device__ __forceinline__ void closest_segment_point(float* out, const float* a, const float* b, const float* pt) {
+  float ab[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, pa[3] = {pt[0] - a[0], pt[1] - a[1], pt[2] - a[2]};
+  float t = clampf(dot3(pa, ab) / (dot3(ab, ab) + 1e-6f), 0.0f, 1.0f);
+  out[0] = a[0] + t * ab[0]; out[1] = a[1] + t * ab[1]; out[2] = a[2] + t * ab[2];
+}
+__device__ __forceinline__ void closest_segment_to_segment(float* best_a, float* best_b, const float* a0, const float* a1,
+                                                           const float* b0, const float* b1) {
+  float dir_a[3] = {a1[0] - a0[0], a1[1] - a0[1], a1[2] - a0[2]}, dir_b[3] = {b1[0] - b0[0], b1[1] - b0[1], b1[2] - b0[2]};
+  float half_a = normalize3(dir_a) * 0.5f, half_b = normalize3(dir_b) * 0.5f;
+  float a_mid[3], b_mid[3], trans[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    a_mid[k] = a0[k] + dir_a[k] * half_a;
+    b_mid[k] = b0[k] + dir_b[k] * half_b;
+    trans[k] = a_mid[k] - b_mid[k];
+  }
+  float dd = dot3(dir_a, dir_b), da_t = dot3(dir_a, trans), db_t = dot3(dir_b, trans);
+  float denom = 1.0f - dd * dd;
+  float orig_ta = (-da_t + dd * db_t) / (denom + 1e-6f);
+  float orig_tb = db_t + orig_ta * dd;
+  float ta = clampf(orig_ta, -half_a, half_a), tb = clampf(orig_tb, -half_b, half_b);
+#pragma unroll
+  for (int k = 0; k < 3; k++) { best_a[k] = a_mid[k] + dir_a[k] * ta; best_b[k] = b_mid[k] + dir_b[k] * tb; }
+  float new_a[3], new_b[3];
+  closest_segment_point(new_a, a0, a1, best_b);
+  closest_segment_point(new_b, b0, b1, best_a);
+  float d1 = 0.0f, d2 = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    d1 += (new_a[k] - best_b[k]) * (new_a[k] - best_b[k]);
+    d2 += (best_a[k] - new_b[k]) * (best_a[k] - new_b[k]);
+  }
+  if (d1 < d2) { best_a[0] = new_a[0]; best_a[1] = new_a[1]; best_a[2] = new_a[2]; }
+  else { best_b[0] = new_b[0]; best_b[1] = new_b[1]; best_b[2] = new_b[2]; }
+}
+// mjx math.make_frame tangents for a unit normal
+__device__ __forceinline__ void make_tangents(const float* n, float* t1, float* t2) {
+  float b[3] = {0.0f, 0.0f, 0.0f};
+  if (-0.5f < n[1] && n[1] < 0.5f) b[1] = 1.0f; else b[2] = 1.0f;
+  float ab = dot3(n, b);
+  b[0] -= n[0] * ab; b[1] -= n[1] * ab; b[2] -= n[2] * ab;
+  normalize3(b);
+  t1[0] = b[0]; t1[1] = b[1]; t1[2] = b[2];
+  cross3(t2, n, b);
+}
+// nearest x >= 0 with pnt + x*vec on a face of the axis-aligned box `size`, else -1 (engine_ray.c ray_box / mjx ray._ray_box)
+__device__ __forceinline__ float ray_box(const float* size, const float* pnt, const float* vec) {
+  float best = -1.0f;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const int i0 = (i == 0) ? 1 : 0, i1 = (i == 2) ? 1 : 2;
+    if (fabsf(vec[i]) <= MINVAL) continue;
+#pragma unroll
+    for (int side = -1; side <= 1; side += 2) {
+      float sol = ((float)side * size[i] - pnt[i]) / vec[i];
+      if (sol >= 0.0f) {
+        float p0 = pnt[i0] + sol * vec[i0], p1 = pnt[i1] + sol * vec[i1];
+        if (fabsf(p0) <= size[i0] && fabsf(p1) <= size[i1] && (best < 0.0f || sol < best)) best = sol;
+      }
+    }
+  }
+  return best;
+}
+
+// ------------------------------------------------------------------------------------------- warp-level linear algebra on WarpS
+// y_i = sum_j M[i][j] x_j ; x is published through vec[VX]
+__device__ __forceinline__ float matvec_M(WarpS& S, int lane, float x) {
+  __syncwarp();
+  S.vec[VX][lane] = (lane < NV) ? x : 0.0f;
+  __syncwarp();
+  float acc = 0.0f;
+  if (lane < NV) {
+    const float4* row = reinterpret_cast<const float4*>(&S.M[lane * NVP]);
+    const float4* xv = reinterpret_cast<const float4*>(&S.vec[VX][0]);
+#pragma unroll
+    for (int g = 0; g < NVP / 4; g++) {
+      float4 m = row[g], xx = xv[g];
+      acc += m.x * xx.x; acc += m.y * xx.y; acc += m.z * xx.z; acc += m.w * xx.w;
+    }
+  }
+  return acc;
+}
+// out[r] = sum_d J[r][d] x_d for all rows (lane-per-row strips); x published through vec[VX]
+__device__ __forceinline__ void rows_times(WarpS& S, int lane, int nrow, float x, float* out /* smem [CAP] */) {
+  __syncwarp();
+  S.vec[VX][lane] = (lane < NV) ? x : 0.0f;
+  __syncwarp();
+  const float4* xv = reinterpret_cast<const float4*>(&S.vec[VX][0]);
+  for (int r = lane; r < nrow; r += 32) {
+    const float4* row = reinterpret_cast<const float4*>(&S.J[r * NVP]);
+    float acc = 0.0f;
+#pragma unroll
+    for (int g = 0; g < NVP / 4; g++) {
+      float4 m = row[g], xx = xv[g];
+      acc += m.x * xx.x; acc += m.y * xx.y; acc += m.z * xx.z; acc += m.w * xx.w;
+    }
+    out[r] = acc;
+  }
+  __syncwarp();
+}
+// y_d = sum_r J[r][d] f_r
+__device__ __forceinline__ float rowsT_times(const WarpS& S, int lane, int nrow, const float* f /* smem [CAP] */) {
+  float acc = 0.0f;
+  if (lane < NVP) {
+    for (int r = 0; r < nrow; r++) acc += S.J[r * NVP + lane] * f[r];
+  }
+  return acc;
+}
+
+// In-register Cholesky of the SPD matrix whose row `lane` is a[0..NV) (lower part used). On return a[k] (k<lane) = L[lane][k],
+// dinv = 1 / L[lane][lane]. Column k is broadcast through S.col (double buffered): 27 SHFL + 27 STS + ~100 LDS.128.
+__device__ __forceinline__ void chol_rows(WarpS& S, int lane, float (&a)[NVP], float& dinv) {
+  dinv = 1.0f;
+#pragma unroll
+  for (int k = 0; k < NV; k++) {
+    float akk = __shfl_sync(FULL, a[k], k);
+    float inv = rsqrtf(akk);
+    float lik = a[k] * inv;          // valid for lane > k; lane k gets sqrt(akk)
+    if (lane == k) dinv = inv;
+    a[k] = lik;
+    if (k + 1 < NV) {
+      float* col = S.col[k & 1];
+      col[lane] = lik;
+      __syncwarp();
+      const float4* cv = reinterpret_cast<const float4*>(col);
+#pragma unroll
+      for (int g = (k + 1) / 4; g < NVP / 4; g++) {
+        float4 c = cv[g];
+        if (4 * g + 0 > k && 4 * g + 0 < NV) a[4 * g + 0] -= lik * c.x;
+        if (4 * g + 1 > k && 4 * g + 1 < NV) a[4 * g + 1] -= lik * c.y;
+        if (4 * g + 2 > k && 4 * g + 2 < NV) a[4 * g + 2] -= lik * c.z;
+        if (4 * g + 3 > k && 4 * g + 3 < NV) a[4 * g + 3] -= lik * c.w;
+      }
+    }
+  }
+}
+// solve (L L^T) x = b with the factor from chol_rows; L rows are spilled to S.L for the backward pass
+__device__ __forceinline__ float chol_solve_rows(WarpS& S, int lane, const float (&a)[NVP], float dinv, float b) {
+  float y = b;
+#pragma unroll
+  for (int k = 0; k < NV; k++) {
+    float yk = __shfl_sync(FULL, y * dinv, k);
+    if (lane > k) y -= a[k] * yk;
+  }
+  y *= dinv;
+  __syncwarp();
+  if (lane < NV) {
+#pragma unroll
+    for (int k = 0; k < NV; k++)
+      if (k < lane) S.L[lane * NV + k] = a[k];
+  }
+  __syncwarp();
+  float x = y;
+#pragma unroll
+  for (int k = NV - 1; k >= 0; k--) {
+    float xk = __shfl_sync(FULL, x * dinv, k);
+    if (lane < k) x -= S.L[k * NV + lane] * xk;
+  }
+  return x * dinv;
+}
+
+struct LSPoint { float alpha, cost, d0, d1; };
+
+// ------------------------------------------------------------------------------------------- the kernel
+template <bool DBG>
+__global__ void __launch_bounds__(MAX_WARPS * 32, 1) mjxb_step_kernel(const DevModel* __restrict__ gmodel, const PairParam* __restrict__ pair_param,
+                                                            StepArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  DevModel& C = *reinterpret_cast<DevModel*>(smem_raw);
+  {
+    const int4* src = reinterpret_cast<const int4*>(gmodel);
+    int4* dst = reinterpret_cast<int4*>(smem_raw);
+    for (int i = threadIdx.x; i < (int)(sizeof(DevModel) / 16); i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  WarpS& S = *reinterpret_cast<WarpS*>(smem_raw + ((sizeof(DevModel) + 15) & ~size_t(15)) + (size_t)warp * sizeof(WarpS));
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const float h = C.timestep;
+  const mjxb_env_config& cfg = C.cfg;
+  const int nbody = C.nbody;
+
+  for (int env = blockIdx.x * nwarp + warp; env < A.n_env; env += gridDim.x * nwarp) {
+    // ---------------------------------------------------------------- load state (lane d <-> qpos[d], qvel[d], ...)
+    int mode = A.mode;
+    float q = 0.0f, v = 0.0f, ws = 0.0f, ctrl = 0.0f, tm = 0.0f, aux = 0.0f, action = 0.0f;
+    int status = 0;
+    if (mode == MODE_ENV_STEP || mode == MODE_PHYS_STEP || mode == MODE_FORWARD) {
+      if (lane < C.nq) q = A.in.qpos[(size_t)env * C.nq + lane];
+      if (lane < NV) { v = A.in.qvel[(size_t)env * NV + lane]; ws = A.in.qacc_warmstart[(size_t)env * NV + lane]; }
+      tm = A.in.time[env];
+      if (A.action != nullptr && lane < C.nu) action = A.action[(size_t)env * C.nu + lane];
+    }
+    if (mode == MODE_ENV_STEP) {
+      if (lane < MJXB_AUX_DIM) aux = A.in.aux[(size_t)env * MJXB_AUX_DIM + lane];
+      float flip = __shfl_sync(FULL, aux, 0);
+      // src/envs.py:339-341 flip + clip
+      int src = lane < C.nu ? cfg.act_perm[lane] : 0;
+      float af = __shfl_sync(FULL, action, src) * (lane < C.nu ? cfg.act_sign[lane] : 0.0f);
+      ctrl = clampf(flip > 0.5f ? af : action, -1.0f, 1.0f);
+    } else {
+      ctrl = action;
+    }
+    uint32_t key0 = 0, key1 = 0;
+    if (A.keys != nullptr) { key0 = A.keys[2 * (size_t)env]; key1 = A.keys[2 * (size_t)env + 1]; }
+    // env-step outputs latched before an in-kernel auto-reset overwrites the state
+    float out_reward = 0.0f, out_term = 0.0f, out_trunc = 0.0f;
+    float qfrc_act = 0.0f;
+    float tgt_x = 0.0f, tgt_y = 0.0f, tgt_z = 0.0f, flip_r = 0.0f;
+    int did_reset = 0;
+
+    for (int istep = 0; istep < A.nsteps; istep++) {
+      if (mode == MODE_SPEED_TEST) {  // mjx_humanoid_speed_test.py:50-53: make_data, qvel[0] = vel
+        q = lane < C.nq ? C.qpos0[lane] : 0.0f;
+        v = (lane == 0) ? A.vel[env] : 0.0f;
+        ws = 0.0f; ctrl = 0.0f; tm = 0.0f;
+      }
+      for (int pass = 0; pass < 2; pass++) {  // pass 1 only for the fused auto-reset
+      if (mode == MODE_ENV_RESET) {
+        // ------------------------------------------------------------ single_reset state init (src/envs.py:117-131,147)
+        uint32_t k1a, k1b, k2a, k2b, k3a, k3b, k4a, k4b;
+        threefry2x32(key0, key1, 0u, 0u, k1a, k1b);
+        threefry2x32(key0, key1, 0u, 1u, k2a, k2b);
+        threefry2x32(key0, key1, 0u, 2u, k3a, k3b);
+        threefry2x32(key0, key1, 0u, 3u, k4a, k4b);
+        flip_r = 0.0f;
+        if (cfg.random_flip) flip_r = jax_uniform(k3a, k3b, 0u, 0.0f, 1.0f) < 0.5f ? 1.0f : 0.0f;
+        q = lane < C.nq ? C.qpos0[lane] : 0.0f;
+        if (lane >= 7 && lane < C.nq) {
+          float nz = __fadd_rn(__fmul_rn(jax_uniform(k1a, k1b, (uint32_t)(lane - 7), 0.0f, 1.0f), 2.0f), -1.0f);
+          q = __fadd_rn(q, __fmul_rn(cfg.random_joint_noise, nz));
+        }
+        v = 0.0f;
+        if (lane < NV) {
+          float nz = __fadd_rn(__fmul_rn(jax_uniform(k2a, k2b, (uint32_t)lane, 0.0f, 1.0f), 2.0f), -1.0f);
+          v = __fmul_rn(cfg.random_vel_noise, nz);
+        }
+        if (cfg.initial_velocity_max > 0.0f) {
+          // target = pelvis + (target_dist, 0): direction is +x up to rounding; vx = vmag*dx/|dx|, vy = vmag*0/|dx|
+          float vmag = jax_uniform(k4a, k4b, 0u, 0.0f, cfg.initial_velocity_max);
+          // dx = (bx + target_dist) - bx is evaluated after kinematics below (needs pelvis x); stash vmag in `action`
+          action = vmag;
+        }
+        ws = 0.0f; ctrl = 0.0f; tm = 0.0f;
+      }
+      // publish state vectors
+      __syncwarp();
+      S.vec[VQPOS][lane] = q;
+      S.vec[VQVEL][lane] = (lane < NV) ? v : 0.0f;
+      S.vec[VCTRL][lane] = ctrl;
+      __syncwarp();
+
+      // ---------------------------------------------------------------- kinematics (level-synchronous over the body tree)
+      if (lane == 0) {
+        S.a.xpos[0][0] = S.a.xpos[0][1] = S.a.xpos[0][2] = 0.0f;
+        S.a.xquat[0][0] = 1.0f; S.a.xquat[0][1] = S.a.xquat[0][2] = S.a.xquat[0][3] = 0.0f;
+      }
+      __syncwarp();
+      for (int lev = 1; lev <= C.maxdepth; lev++) {
+        if (lane < nbody && C.body_depth[lane] == lev) {
+          const int b = lane, p = C.body_parent[b];
+          float pq[4] = {S.a.xquat[p][0], S.a.xquat[p][1], S.a.xquat[p][2], S.a.xquat[p][3]};
+          float pos[3], quat[4], t[3];
+          rotq(t, C.body_pos[b], pq);
+          pos[0] = S.a.xpos[p][0] + t[0]; pos[1] = S.a.xpos[p][1] + t[1]; pos[2] = S.a.xpos[p][2] + t[2];
+          quat_mul(quat, pq, C.body_quat[b]);
+          for (int j = C.body_jntadr[b]; j < C.body_jntadr[b] + C.body_jntnum[b]; j++) {
+            const int qa = C.jnt_qposadr[j], da = C.jnt_dofadr[j];
+            if (C.jnt_type[j] == 0) {
+              pos[0] = S.vec[VQPOS][qa]; pos[1] = S.vec[VQPOS][qa + 1]; pos[2] = S.vec[VQPOS][qa + 2];
+              float w = S.vec[VQPOS][qa + 3], x = S.vec[VQPOS][qa + 4], y = S.vec[VQPOS][qa + 5], z = S.vec[VQPOS][qa + 6];
+              float n = sqrtf(w * w + x * x + y * y + z * z);
+              float dn = n + (n == 0.0f ? 1e-6f : 0.0f);
+              quat[0] = w / dn; quat[1] = x / dn; quat[2] = y / dn; quat[3] = z / dn;
+              S.vec[VQPOS][qa + 3] = quat[0]; S.vec[VQPOS][qa + 4] = quat[1]; S.vec[VQPOS][qa + 5] = quat[2]; S.vec[VQPOS][qa + 6] = quat[3];
+            } else {
+              float anchor[3], axis[3];
+              rotq(t, C.jnt_pos[j], quat);
+              anchor[0] = t[0] + pos[0]; anchor[1] = t[1] + pos[1]; anchor[2] = t[2] + pos[2];
+              rotq(axis, C.jnt_axis[j], quat);
+              S.cdof[da][0] = axis[0]; S.cdof[da][1] = axis[1]; S.cdof[da][2] = axis[2];
+              S.cdof[da][3] = anchor[0]; S.cdof[da][4] = anchor[1]; S.cdof[da][5] = anchor[2];
+              float ang = S.vec[VQPOS][qa] - C.qpos0[qa], sn, cs;
+              sincosf(ang * 0.5f, &sn, &cs);
+              float ql[4] = {cs, C.jnt_axis[j][0] * sn, C.jnt_axis[j][1] * sn, C.jnt_axis[j][2] * sn}, qn[4];
+              quat_mul(qn, quat, ql);
+              quat[0] = qn[0]; quat[1] = qn[1]; quat[2] = qn[2]; quat[3] = qn[3];
+              rotq(t, C.jnt_pos[j], quat);
+              pos[0] = anchor[0] - t[0]; pos[1] = anchor[1] - t[1]; pos[2] = anchor[2] - t[2];
+            }
+          }
+          S.a.xpos[b][0] = pos[0]; S.a.xpos[b][1] = pos[1]; S.a.xpos[b][2] = pos[2];
+          S.a.xquat[b][0] = quat[0]; S.a.xquat[b][1] = quat[1]; S.a.xquat[b][2] = quat[2]; S.a.xquat[b][3] = quat[3];
+        }
+        __syncwarp();
+      }
+      q = S.vec[VQPOS][lane];  // kinematics normalised the free-joint quaternion in place
+
+      if (mode == MODE_ENV_RESET && cfg.initial_velocity_max > 0.0f) {  // src/envs.py:136-152
+        float bx = S.a.xpos[cfg.pelvis_body_id][0], by = S.a.xpos[cfg.pelvis_body_id][1];
+        float tx = bx + cfg.target_dist, ty = by;
+        float dx = tx - bx, dy = ty - by;
+        float dist_xy = sqrtf(dx * dx + dy * dy);
+        float vmag = action;
+        float vx = dist_xy > 1e-6f ? __fdiv_rn(__fmul_rn(vmag, dx), dist_xy) : 0.0f;
+        float vy = dist_xy > 1e-6f ? __fdiv_rn(__fmul_rn(vmag, dy), dist_xy) : 0.0f;
+        if (lane == 0) v = vx;
+        if (lane == 1) v = vy;
+        __syncwarp();
+        S.vec[VQVEL][lane] = (lane < NV) ? v : 0.0f;
+        __syncwarp();
+      }
+
+      // ---------------------------------------------------------------- geoms, sites, frames the env layer reads
+      if (lane < C.ngeom) {
+        const int b = C.geom_body[lane];
+        float bq[4] = {S.a.xquat[b][0], S.a.xquat[b][1], S.a.xquat[b][2], S.a.xquat[b][3]}, t[3];
+        rotq(t, C.geom_pos[lane], bq);
+        S.gpos[lane][0] = S.a.xpos[b][0] + t[0]; S.gpos[lane][1] = S.a.xpos[b][1] + t[1]; S.gpos[lane][2] = S.a.xpos[b][2] + t[2];
+        rotq(t, C.geom_axis[lane], bq);
+        S.gaxis[lane][0] = t[0]; S.gaxis[lane][1] = t[1]; S.gaxis[lane][2] = t[2];
+      }
+      if (lane < C.nsite) {
+        const int b = C.site_body[lane];
+        float bq[4] = {S.a.xquat[b][0], S.a.xquat[b][1], S.a.xquat[b][2], S.a.xquat[b][3]}, t[3], sq[4];
+        rotq(t, C.site_pos[lane], bq);
+        S.site_xpos[lane][0] = S.a.xpos[b][0] + t[0]; S.site_xpos[lane][1] = S.a.xpos[b][1] + t[1]; S.site_xpos[lane][2] = S.a.xpos[b][2] + t[2];
+        quat_mul(sq, bq, C.site_quat[lane]);
+        quat_to_mat(S.site_xmat[lane], sq);
+      }
+      if (lane == 31) {
+        const int pb = cfg.pelvis_body_id, hb = cfg.head_body_id;
+#pragma unroll
+        for (int k = 0; k < 3; k++) { S.pelvis_pos[k] = S.a.xpos[pb][k]; S.head_pos[k] = S.a.xpos[hb][k]; }
+#pragma unroll
+        for (int k = 0; k < 4; k++) S.pelvis_quat[k] = S.a.xquat[pb][k];
+      }
+      if (DBG) {
+        if (A.dbg.xpos && lane < nbody) for (int k = 0; k < 3; k++) A.dbg.xpos[((size_t)env * nbody + lane) * 3 + k] = S.a.xpos[lane][k];
+        if (A.dbg.xquat && lane < nbody) for (int k = 0; k < 4; k++) A.dbg.xquat[((size_t)env * nbody + lane) * 4 + k] = S.a.xquat[lane][k];
+      }
+
+      // ---------------------------------------------------------------- com_pos: subtree com of the single tree, cinert, cdof
+      float com[3];
+      {
+        float xip[3] = {0.0f, 0.0f, 0.0f}, mass = 0.0f, R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        if (lane < nbody) {
+          quat_to_mat(R, S.a.xquat[lane]);
+          const float* ip = C.body_ipos[lane];
+          xip[0] = S.a.xpos[lane][0] + R[0] * ip[0] + R[1] * ip[1] + R[2] * ip[2];
+          xip[1] = S.a.xpos[lane][1] + R[3] * ip[0] + R[4] * ip[1] + R[5] * ip[2];
+          xip[2] = S.a.xpos[lane][2] + R[6] * ip[0] + R[7] * ip[1] + R[8] * ip[2];
+          mass = C.body_mass[lane];
+        }
+        float inv_m = 1.0f / fmaxf(C.total_mass, MINVAL);
+        com[0] = warp_sum(mass * xip[0]) * inv_m;
+        com[1] = warp_sum(mass * xip[1]) * inv_m;
+        com[2] = warp_sum(mass * xip[2]) * inv_m;
+        if (lane < nbody) {
+          float off[3] = {xip[0] - com[0], xip[1] - com[1], xip[2] - com[2]};
+          const float* bi = C.body_inertia[lane];
+          float I[9] = {bi[0], bi[3], bi[4], bi[3], bi[1], bi[5], bi[4], bi[5], bi[2]}, XI[9], Iw[9];
+#pragma unroll
+          for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) XI[3 * r + c] = R[3 * r] * I[c] + R[3 * r + 1] * I[3 + c] + R[3 * r + 2] * I[6 + c];
+#pragma unroll
+          for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) Iw[3 * r + c] = XI[3 * r] * R[3 * c] + XI[3 * r + 1] * R[3 * c + 1] + XI[3 * r + 2] * R[3 * c + 2];
+          float oo = dot3(off, off);
+          float* ci = S.a.cinert[lane];
+          ci[0] = Iw[0] + mass * (oo - off[0] * off[0]);
+          ci[1] = Iw[4] + mass * (oo - off[1] * off[1]);
+          ci[2] = Iw[8] + mass * (oo - off[2] * off[2]);
+          ci[3] = Iw[1] - mass * off[0] * off[1];
+          ci[4] = Iw[2] - mass * off[0] * off[2];
+          ci[5] = Iw[5] - mass * off[1] * off[2];
+          ci[6] = mass * off[0]; ci[7] = mass * off[1]; ci[8] = mass * off[2];
+          ci[9] = mass;
+        }
+        if (lane < NV) {
+          const int j = C.dof_jnt[lane], b = C.dof_body[lane];
+          float* cd = S.cdof[lane];
+          if (C.jnt_type[j] == 0) {
+            const int k = lane - C.jnt_dofadr[j];
+            if (k < 3) {
+              cd[0] = cd[1] = cd[2] = 0.0f;
+              cd[3] = k == 0 ? 1.0f : 0.0f; cd[4] = k == 1 ? 1.0f : 0.0f; cd[5] = k == 2 ? 1.0f : 0.0f;
+            } else {
+              float Rb[9];
+              quat_to_mat(Rb, S.a.xquat[b]);
+              float ax[3];  // column (k-3) of the body rotation, selected without dynamic register indexing
+              ax[0] = k == 3 ? Rb[0] : k == 4 ? Rb[1] : Rb[2];
+              ax[1] = k == 3 ? Rb[3] : k == 4 ? Rb[4] : Rb[5];
+              ax[2] = k == 3 ? Rb[6] : k == 4 ? Rb[7] : Rb[8];
+              float off[3] = {com[0] - S.a.xpos[b][0], com[1] - S.a.xpos[b][1], com[2] - S.a.xpos[b][2]};
+              cd[0] = ax[0]; cd[1] = ax[1]; cd[2] = ax[2];
+              cross3(cd + 3, ax, off);
+            }
+          } else {
+            float ax[3] = {cd[0], cd[1], cd[2]}, off[3] = {com[0] - cd[3], com[1] - cd[4], com[2] - cd[5]};
+            cross3(cd + 3, ax, off);
+          }
+        }
+      }
+      __syncwarp();
+
+      // ---------------------------------------------------------------- com_vel + cacc (root -> leaf), body-local cfrc
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) { S.a.cvel[0][k] = 0.0f; S.a.cacc[0][k] = 0.0f; }
+        S.a.cacc[0][3] = -C.gravity[0]; S.a.cacc[0][4] = -C.gravity[1]; S.a.cacc[0][5] = -C.gravity[2];
+      }
+      __syncwarp();
+      for (int lev = 1; lev <= C.maxdepth; lev++) {
+        if (lane < nbody && C.body_depth[lane] == lev) {
+          const int b = lane, p = C.body_parent[b];
+          float cv[6], ca[6], cdd[6];
+#pragma unroll
+          for (int k = 0; k < 6; k++) { cv[k] = S.a.cvel[p][k]; ca[k] = S.a.cacc[p][k]; }
+          for (int j = C.body_jntadr[b]; j < C.body_jntadr[b] + C.body_jntnum[b]; j++) {
+            const int da = C.jnt_dofadr[j];
+            if (C.jnt_type[j] == 0) {
+              for (int i = 0; i < 3; i++) {
+                float qv = S.vec[VQVEL][da + i];
+#pragma unroll
+                for (int k = 0; k < 6; k++) cv[k] += S.cdof[da + i][k] * qv;
+              }
+              for (int i = 3; i < 6; i++) {
+                float qv = S.vec[VQVEL][da + i];
+                motion_cross(cdd, cv, S.cdof[da + i]);
+#pragma unroll
+                for (int k = 0; k < 6; k++) ca[k] += cdd[k] * qv;
+              }
+              for (int i = 3; i < 6; i++) {
+                float qv = S.vec[VQVEL][da + i];
+#pragma unroll
+                for (int k = 0; k < 6; k++) cv[k] += S.cdof[da + i][k] * qv;
+              }
+            } else {
+              float qv = S.vec[VQVEL][da];
+              motion_cross(cdd, cv, S.cdof[da]);
+#pragma unroll
+              for (int k = 0; k < 6; k++) { ca[k] += cdd[k] * qv; cv[k] += S.cdof[da][k] * qv; }
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 6; k++) { S.a.cvel[b][k] = cv[k]; S.a.cacc[b][k] = ca[k]; }
+        }
+        __syncwarp();
+      }
+      if (lane < nbody) {  // f = I*cacc + cvel x* (I*cvel), written over cacc[b]
+        float ci[10], ca[6], cv[6], f1[6], iv[6], f2[6];
+#pragma unroll
+        for (int k = 0; k < 10; k++) ci[k] = S.a.cinert[lane][k];
+#pragma unroll
+        for (int k = 0; k < 6; k++) { ca[k] = S.a.cacc[lane][k]; cv[k] = S.a.cvel[lane][k]; }
+        inert_mul(f1, ci, ca);
+        inert_mul(iv, ci, cv);
+        motion_cross_force(f2, cv, iv);
+#pragma unroll
+        for (int k = 0; k < 6; k++) S.a.cacc[lane][k] = (lane == 0) ? 0.0f : f1[k] + f2[k];
+      }
+      __syncwarp();
+      {  // subtree sums (bodies are in DFS order: a subtree is the contiguous id range [b, subtree_end[b]))
+        float crb[10], cf[6];
+#pragma unroll
+        for (int k = 0; k < 10; k++) crb[k] = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 6; k++) cf[k] = 0.0f;
+        if (lane >= 1 && lane < nbody) {
+          for (int c = lane; c < C.body_subtree_end[lane]; c++) {
+#pragma unroll
+            for (int k = 0; k < 10; k++) crb[k] += S.a.cinert[c][k];
+#pragma unroll
+            for (int k = 0; k < 6; k++) cf[k] += S.a.cacc[c][k];
+          }
+        }
+        __syncwarp();
+        if (lane < nbody) {
+#pragma unroll
+          for (int k = 0; k < 10; k++) S.a.cinert[lane][k] = crb[k];
+#pragma unroll
+          for (int k = 0; k < 6; k++) S.a.cvel[lane][k] = cf[k];
+        }
+      }
+      for (int i = lane; i < NV * NVP; i += 32) S.M[i] = 0.0f;
+      __syncwarp();
+
+      // ---------------------------------------------------------------- crb mass matrix, bias, passive, actuation
+      float qfs = 0.0f;  // qfrc_smooth
+      if (lane < NV) {
+        float cd[6], f[6];
+#pragma unroll
+        for (int k = 0; k < 6; k++) cd[k] = S.cdof[lane][k];
+        inert_mul(f, S.a.cinert[C.dof_body[lane]], cd);
+        for (int j = lane; j >= 0; j = C.dof_parent[j]) {
+          float s = 0.0f;
+#pragma unroll
+          for (int k = 0; k < 6; k++) s += S.cdof[j][k] * f[k];
+          if (j == lane) s += C.dof_armature[lane];
+          S.M[lane * NVP + j] = s;
+          S.M[j * NVP + lane] = s;
+        }
+        float bias = 0.0f;
+        const float* cf = S.a.cvel[C.dof_body[lane]];
+#pragma unroll
+        for (int k = 0; k < 6; k++) bias += cd[k] * cf[k];
+        float passive = 0.0f;
+        const int qa = C.dof_qadr[lane];
+        if (qa >= 0) passive = -C.dof_stiffness[lane] * (S.vec[VQPOS][qa] - C.qpos_spring[qa]) - C.dof_damping[lane] * v;
+        qfrc_act = 0.0f;
+        const int u = C.dof_act[lane];
+        if (u >= 0) qfrc_act = C.dof_gear[lane] * clampf(S.vec[VCTRL][u], C.dof_ctrl_lo[lane], C.dof_ctrl_hi[lane]);
+        qfs = passive - bias + qfrc_act;
+        if (DBG) {
+          if (A.dbg.qfrc_bias) A.dbg.qfrc_bias[(size_t)env * NV + lane] = bias;
+          if (A.dbg.qfrc_passive) A.dbg.qfrc_passive[(size_t)env * NV + lane] = passive;
+          if (A.dbg.qfrc_actuator) A.dbg.qfrc_actuator[(size_t)env * NV + lane] = qfrc_act;
+        }
+      }
+      __syncwarp();
+      if (DBG && A.dbg.qM) {
+        for (int i = lane; i < NV * NV; i += 32) A.dbg.qM[(size_t)env * NV * NV + i] = S.M[(i / NV) * NVP + (i % NV)];
+      }
+
+      // ---------------------------------------------------------------- collision: lane per geom pair, candidates compacted by ballot
+      int ncc = 0;
+      for (int base = 0; base < C.npair; base += 32) {
+        const int p = base + lane;
+        const bool valid = p < C.npair;
+        float dist[2] = {1.0f, 1.0f}, cpos[2][3] = {{0, 0, 0}, {0, 0, 0}}, n[3] = {0, 0, 1}, t1[3] = {0, 0, 0}, t2[3] = {0, 0, 0};
+        int kind = -1, condim = 1;
+        if (valid) {
+          const uint32_t w0 = C.pair_w0[p];
+          const int g1 = w0 & 0xff, g2 = (w0 >> 8) & 0xff;
+          kind = (w0 >> 16) & 0xff; condim = (w0 >> 24) & 0xff;
+          float p1[3] = {S.gpos[g1][0], S.gpos[g1][1], S.gpos[g1][2]}, p2[3] = {S.gpos[g2][0], S.gpos[g2][1], S.gpos[g2][2]};
+          float ax1[3] = {S.gaxis[g1][0], S.gaxis[g1][1], S.gaxis[g1][2]}, ax2[3] = {S.gaxis[g2][0], S.gaxis[g2][1], S.gaxis[g2][2]};
+          const float r1 = C.geom_rad[g1], r2 = C.geom_rad[g2], l1 = C.geom_half[g1], l2 = C.geom_half[g2];
+          if (kind == PAIR_PLANE_CAPSULE || kind == PAIR_PLANE_SPHERE) {
+            n[0] = ax1[0]; n[1] = ax1[1]; n[2] = ax1[2];
+            if (kind == PAIR_PLANE_CAPSULE) {
+              float na = dot3(ax1, ax2);
+              float b[3] = {ax2[0] - ax1[0] * na, ax2[1] - ax1[1] * na, ax2[2] - ax1[2] * na};
+              float bn = normalize3(b);
+              if (bn < 0.5f) {
+                b[0] = 0.0f; b[1] = 0.0f; b[2] = 0.0f;
+                if (-0.5f < ax1[1] && ax1[1] < 0.5f) b[1] = 1.0f; else b[2] = 1.0f;
+              }
+              t1[0] = b[0]; t1[1] = b[1]; t1[2] = b[2];
+              cross3(t2, ax1, b);
+#pragma unroll
+              for (int e = 0; e < 2; e++) {
+                const float sg = e == 0 ? 1.0f : -1.0f;
+                float sp[3] = {p2[0] + sg * (ax2[0] * l2), p2[1] + sg * (ax2[1] * l2), p2[2] + sg * (ax2[2] * l2)};
+                float df[3] = {sp[0] - p1[0], sp[1] - p1[1], sp[2] - p1[2]};
+                float d_ = dot3(df, ax1) - r2;
+                dist[e] = d_;
+                float s_ = r2 + 0.5f * d_;
+                cpos[e][0] = sp[0] - ax1[0] * s_; cpos[e][1] = sp[1] - ax1[1] * s_; cpos[e][2] = sp[2] - ax1[2] * s_;
+              }
+            } else {
+              float df[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+              float d_ = dot3(df, ax1) - r2;
+              dist[0] = d_;
+              float s_ = r2 + 0.5f * d_;
+              cpos[0][0] = p2[0] - ax1[0] * s_; cpos[0][1] = p2[1] - ax1[1] * s_; cpos[0][2] = p2[2] - ax1[2] * s_;
+              make_tangents(n, t1, t2);
+            }
+          } else {
+            float pa[3] = {p1[0], p1[1], p1[2]}, pb[3] = {p2[0], p2[1], p2[2]};
+            if (kind == PAIR_SPHERE_CAPSULE) {
+              float a[3] = {p2[0] - ax2[0] * l2, p2[1] - ax2[1] * l2, p2[2] - ax2[2] * l2};
+              float b[3] = {p2[0] + ax2[0] * l2, p2[1] + ax2[1] * l2, p2[2] + ax2[2] * l2};
+              closest_segment_point(pb, a, b, p1);
+            } else if (kind == PAIR_CAPSULE_CAPSULE) {
+              float a0[3] = {p1[0] - ax1[0] * l1, p1[1] - ax1[1] * l1, p1[2] - ax1[2] * l1};
+              float a1[3] = {p1[0] + ax1[0] * l1, p1[1] + ax1[1] * l1, p1[2] + ax1[2] * l1};
+              float b0[3] = {p2[0] - ax2[0] * l2, p2[1] - ax2[1] * l2, p2[2] - ax2[2] * l2};
+              float b1[3] = {p2[0] + ax2[0] * l2, p2[1] + ax2[1] * l2, p2[2] + ax2[2] * l2};
+              closest_segment_to_segment(pa, pb, a0, a1, b0, b1);
+            }
+            sphere_sphere(dist[0], cpos[0], n, pa, r1, pb, r2);
+            if (condim > 1) make_tangents(n, t1, t2);
+          }
+          if (DBG) {
+            const int c0 = C.pair_w1[p] & 0xffff;
+            const int ne = (kind == PAIR_PLANE_CAPSULE) ? 2 : 1;
+            for (int e = 0; e < ne; e++) {
+              if (A.dbg.con_dist) A.dbg.con_dist[(size_t)env * C.ncon + c0 + e] = dist[e];
+              if (A.dbg.con_pos) for (int k = 0; k < 3; k++) A.dbg.con_pos[((size_t)env * C.ncon + c0 + e) * 3 + k] = cpos[e][k];
+              if (A.dbg.con_normal) for (int k = 0; k < 3; k++) A.dbg.con_normal[((size_t)env * C.ncon + c0 + e) * 3 + k] = n[k];
+            }
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const bool cand = valid && (e == 0 || kind == PAIR_PLANE_CAPSULE) && dist[e] < 0.0f;
+          const unsigned mk = __ballot_sync(FULL, cand);
+          const int idx = ncc + __popc(mk & lt_mask);
+          if (cand && idx < MAXCC) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) { S.cc_n[idx][k] = n[k]; S.cc_t1[idx][k] = t1[k]; S.cc_t2[idx][k] = t2[k]; S.cc_pos[idx][k] = cpos[e][k]; }
+            S.cc_dist[idx] = dist[e];
+            S.cc_pair[idx] = p | (e << 16) | (condim << 20);
+          }
+          ncc += __popc(mk);
+        }
+      }
+      if (ncc > MAXCC) { status |= MJXB_STATUS_ROW_SPILL; ncc = MAXCC; }
+      __syncwarp();
+
+      // ---------------------------------------------------------------- constraint rows: joint limits, tendon limits, contacts
+      int nrow = 0;
+      {
+        // joint limits
+        bool cand = false;
+        float pos = 0.0f, sgn = 1.0f;
+        if (lane < C.nlimit) {
+          float qq = S.vec[VQPOS][C.lim_qadr[lane]];
+          float dmin = qq - C.lim_range[lane][0], dmax = C.lim_range[lane][1] - qq;
+          pos = fminf(dmin, dmax);
+          sgn = dmin < dmax ? 1.0f : -1.0f;
+          cand = pos < 0.0f;
+        }
+        unsigned mk = __ballot_sync(FULL, cand);
+        int r = nrow + __popc(mk & lt_mask);
+        if (cand && r < CAP) { S.rinfo[r] = ROW_LIMIT | (lane << 2) | (sgn < 0.0f ? 1 << 10 : 0); S.rJaref[r] = pos; }
+        nrow += __popc(mk);
+        // tendon limits
+        cand = false;
+        if (lane < C.ntlimit) {
+          float len = 0.0f;
+          for (int w = 0; w < C.ten_nwrap[lane]; w++) len += C.ten_coef[lane][w] * S.vec[VQPOS][C.ten_qpos[lane][w]];
+          float dmin = len - C.ten_range[lane][0], dmax = C.ten_range[lane][1] - len;
+          pos = fminf(dmin, dmax);
+          sgn = dmin < dmax ? 1.0f : -1.0f;
+          cand = pos < 0.0f;
+        }
+        mk = __ballot_sync(FULL, cand);
+        r = nrow + __popc(mk & lt_mask);
+        if (cand && r < CAP) { S.rinfo[r] = ROW_TENDON | (lane << 2) | (sgn < 0.0f ? 1 << 10 : 0); S.rJaref[r] = pos; }
+        nrow += __popc(mk);
+        // contacts: exclusive scan of rows per candidate
+        int nr = 0;
+        if (lane < ncc) nr = ((S.cc_pair[lane] >> 20) > 1) ? 4 : 1;
+        int scan = nr;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          int t = __shfl_up_sync(FULL, scan, o);
+          if (lane >= o) scan += t;
+        }
+        int rbase = nrow + scan - nr;
+        bool fits = (lane < ncc) && (rbase + nr <= CAP);
+        unsigned fm = __ballot_sync(FULL, fits);
+        int nfit = __popc(fm);  // candidates are dropped from the tail
+        if (lane < ncc) S.cc_row[lane] = fits ? rbase : -1;
+        int total = __shfl_sync(FULL, scan, 31);
+        if (nrow + total > CAP || nrow > CAP) {
+          status |= MJXB_STATUS_ROW_SPILL;
+          ncc = nfit;
+          nrow = min(nrow, CAP);
+          total = (nfit > 0) ? (__shfl_sync(FULL, scan, max(nfit - 1, 0))) : 0;
+        }
+        const int nrow_lim = nrow;
+        nrow += total;
+        __syncwarp();
+        // cooperative Jacobian rows: limits / tendons
+        for (int rr = 0; rr < nrow_lim; rr++) {
+          const int info = S.rinfo[rr];
+          const int idx = (info >> 2) & 0xff;
+          const float sg = (info & (1 << 10)) ? -1.0f : 1.0f;
+          float val = 0.0f;
+          if ((info & 3) == ROW_LIMIT) {
+            val = (lane == C.lim_dof[idx]) ? sg : 0.0f;
+          } else {
+            for (int w = 0; w < C.ten_nwrap[idx]; w++)
+              if (C.ten_dof[idx][w] == lane) val += sg * C.ten_coef[idx][w];
+          }
+          if (lane < NVP) S.J[rr * NVP + lane] = val;
+        }
+        // contact rows: lane d evaluates its column of the point Jacobian difference (mjx support.jac)
+        float cdl[6] = {0, 0, 0, 0, 0, 0};
+        if (lane < NV) {
+#pragma unroll
+          for (int k = 0; k < 6; k++) cdl[k] = S.cdof[lane][k];
+        }
+        for (int c = 0; c < ncc; c++) {
+          const int pr = S.cc_pair[c], p = pr & 0xffff, rb = S.cc_row[c];
+          const uint32_t w0 = C.pair_w0[p];
+          const int b1 = C.geom_body[w0 & 0xff], b2 = C.geom_body[(w0 >> 8) & 0xff];
+          const bool c3 = (pr >> 20) > 1;
+          float off[3] = {S.cc_pos[c][0] - com[0], S.cc_pos[c][1] - com[1], S.cc_pos[c][2] - com[2]};
+          float jc[3], sgnb = 0.0f;
+          cross3(jc, cdl, off);
+          jc[0] += cdl[3]; jc[1] += cdl[4]; jc[2] += cdl[5];
+          if ((C.body_dofmask[b2] >> lane) & 1u) sgnb += 1.0f;
+          if ((C.body_dofmask[b1] >> lane) & 1u) sgnb -= 1.0f;
+          jc[0] *= sgnb; jc[1] *= sgnb; jc[2] *= sgnb;
+          float jn = dot3(S.cc_n[c], jc);
+          if (lane < NVP) {
+            if (!c3) {
+              S.J[rb * NVP + lane] = jn;
+            } else {
+              const float mu = pair_param[p].mu;
+              float j1 = dot3(S.cc_t1[c], jc) * mu, j2 = dot3(S.cc_t2[c], jc) * mu;
+              S.J[(rb + 0) * NVP + lane] = jn + j1;
+              S.J[(rb + 1) * NVP + lane] = jn - j1;
+              S.J[(rb + 2) * NVP + lane] = jn + j2;
+              S.J[(rb + 3) * NVP + lane] = jn - j2;
+            }
+          }
+          if (lane < (c3 ? 4 : 1)) {
+            S.rinfo[rb + lane] = (c3 ? ROW_CON3 : ROW_CON1) | (c << 2) | (lane << 11);
+            S.rJaref[rb + lane] = S.cc_dist[c];
+          }
+        }
+        __syncwarp();
+        // per-row impedance / reference acceleration (lane per row)
+        const float4* qv4 = reinterpret_cast<const float4*>(&S.vec[VQVEL][0]);
+        for (int rr = lane; rr < nrow; rr += 32) {
+          const int info = S.rinfo[rr], kind = info & 3, idx = (info >> 2) & 0xff;
+          const float rpos = S.rJaref[rr];
+          float invw, solref[2], solimp[5];
+          int efc_row;
+          if (kind == ROW_LIMIT) {
+            invw = C.lim_invweight[idx]; solref[0] = C.lim_solref[idx][0]; solref[1] = C.lim_solref[idx][1];
+#pragma unroll
+            for (int k = 0; k < 5; k++) solimp[k] = C.lim_solimp[idx][k];
+            efc_row = C.lim_row[idx];
+          } else if (kind == ROW_TENDON) {
+            invw = C.ten_invweight[idx]; solref[0] = C.ten_solref[idx][0]; solref[1] = C.ten_solref[idx][1];
+#pragma unroll
+            for (int k = 0; k < 5; k++) solimp[k] = C.ten_solimp[idx][k];
+            efc_row = C.ten_row[idx];
+          } else {
+            const int pr = S.cc_pair[idx], p = pr & 0xffff, e = (pr >> 16) & 0xf;
+            const PairParam pp = pair_param[p];
+            invw = pp.invweight; solref[0] = pp.solref[0]; solref[1] = pp.solref[1];
+#pragma unroll
+            for (int k = 0; k < 5; k++) solimp[k] = pp.solimp[k];
+            const int efc0 = C.pair_w1[p] >> 16;
+            efc_row = (kind == ROW_CON1) ? efc0 + e : efc0 + 4 * e + ((info >> 11) & 3);
+          }
+          float kk, bb, imp;
+          kbi(h, solref, solimp, rpos, kk, bb, imp);
+          float rr_ = fmaxf(invw * (1.0f - imp) / imp, MINVAL);
+          const float4* row = reinterpret_cast<const float4*>(&S.J[rr * NVP]);
+          float vel = 0.0f;
+#pragma unroll
+          for (int g = 0; g < NVP / 4; g++) {
+            float4 m = row[g], xx = qv4[g];
+            vel += m.x * xx.x; vel += m.y * xx.y; vel += m.z * xx.z; vel += m.w * xx.w;
+          }
+          const float D = 1.0f / rr_, aref = -bb * vel - kk * imp * rpos;
+          S.rD[rr] = D;
+          S.raref[rr] = aref;
+          S.rinfo[rr] = (info & 0xffff) | (efc_row << 16);
+          if (DBG) {
+            if (A.dbg.efc_pos) A.dbg.efc_pos[(size_t)env * C.nefc + efc_row] = rpos;
+            if (A.dbg.efc_D) A.dbg.efc_D[(size_t)env * C.nefc + efc_row] = D;
+            if (A.dbg.efc_aref) A.dbg.efc_aref[(size_t)env * C.nefc + efc_row] = aref;
+          }
+        }
+        __syncwarp();
+      }
+
+      // ---------------------------------------------------------------- solve: one factor/solve code instance drives
+      //   phase 0: qacc_smooth = M^-1 qfrc_smooth         (mjx smooth.factor_m/solve_m)
+      //   phase 1: Newton  Mgrad = (M + J^T D_act J)^-1 grad (mjx solver._update_gradient), repeated
+      //   phase 2: qacc'   = (M + h*damping)^-1 (qfrc_smooth + qfrc_constraint)   (mjx forward.implicit / euler)
+      float qas = 0.0f, qacc = 0.0f, Ma = 0.0f, qfc = 0.0f, grad = 0.0f, search = 0.0f;
+      float gauss = 0.0f, cost = 0.0f, prev_cost = 0.0f;
+      unsigned act0 = 0u, act1 = 0u;  // active mask of rows 0..31 / 32..63
+      int niter = 0, phase = 0;
+      const float scale = 1.0f / (C.meaninertia * (float)max(1, C.nv));
+      float qacc_int = 0.0f;
+      const bool integrate_pass = (mode == MODE_ENV_STEP || mode == MODE_PHYS_STEP || mode == MODE_SPEED_TEST);
+
+      // update_constraint (mjx solver._update_constraint) on the current Jaref/Ma/qacc
+      auto update_constraint = [&]() {
+        float cs = 0.0f;
+        act0 = 0u; act1 = 0u;
+#pragma unroll
+        for (int s = 0; s < NSTRIP; s++) {
+          const int r = s * 32 + lane;
+          bool active = false;
+          if (r < nrow) {
+            const float ja = S.rJaref[r], D = S.rD[r];
+            active = ja < 0.0f;
+            S.rforce[r] = active ? -D * ja : 0.0f;
+            cs += active ? D * ja * ja : 0.0f;
+          }
+          const unsigned mk = __ballot_sync(FULL, active);
+          if (s == 0) act0 = mk; else act1 = mk;
+        }
+        __syncwarp();
+        qfc = rowsT_times(S, lane, nrow, S.rforce);
+        gauss = 0.5f * warp_sum((lane < NV) ? (Ma - qfs) * (qacc - qas) : 0.0f);
+        prev_cost = cost;
+        cost = 0.5f * warp_sum(cs) + gauss;
+      };
+
+      while (true) {
+        if (phase == 1) {  // mjx solver.solve cond(): evaluated before paying for the next factorisation
+          bool done;
+          if (C.iterations == 1) {
+            done = niter >= 1;
+          } else {
+            const float improvement = (prev_cost - cost) * scale;
+            const float gradient = sqrtf(warp_sum((lane < NV) ? grad * grad : 0.0f)) * scale;
+            done = (niter >= C.iterations) || (improvement < C.tolerance) || (gradient < C.tolerance);
+            if (niter >= C.iterations && !(improvement < C.tolerance) && !(gradient < C.tolerance)) status |= MJXB_STATUS_MAXITER;
+          }
+          if (done) {
+            if (!integrate_pass) break;
+            phase = 2;
+          }
+        }
+        // ---- assemble the rows of the system matrix in registers
+        float a[NVP];
+        {
+          const float4* row = reinterpret_cast<const float4*>(&S.M[(lane < NV ? lane : 0) * NVP]);
+#pragma unroll
+          for (int g = 0; g < NVP / 4; g++) {
+            float4 m = row[g];
+            a[4 * g] = m.x; a[4 * g + 1] = m.y; a[4 * g + 2] = m.z; a[4 * g + 3] = m.w;
+          }
+        }
+        if (phase == 2) {
+          const float hd = (lane < NV) ? h * C.dof_damping[lane] : 0.0f;
+#pragma unroll
+          for (int j = 0; j < NV; j++) a[j] += (j == lane) ? hd : 0.0f;
+        }
+        if (phase == 1) {
+          for (int r = 0; r < nrow; r++) {
+            const bool on = (r < 32) ? ((act0 >> r) & 1u) : ((act1 >> (r - 32)) & 1u);
+            if (!on) continue;
+            const float w = S.rD[r] * S.J[r * NVP + (lane < NVP ? lane : 0)];
+            const float4* jr = reinterpret_cast<const float4*>(&S.J[r * NVP]);
+#pragma unroll
+            for (int g = 0; g < NVP / 4; g++) {
+              float4 jj = jr[g];
+              a[4 * g] += w * jj.x; a[4 * g + 1] += w * jj.y; a[4 * g + 2] += w * jj.z; a[4 * g + 3] += w * jj.w;
+            }
+          }
+        }
+        if (lane >= NV) {  // idle lanes: identity rows keep the arithmetic finite
+#pragma unroll
+          for (int j = 0; j < NVP; j++) a[j] = 0.0f;
+        }
+        const float rhs = (phase == 0) ? qfs : (phase == 1) ? grad : (qfs + qfc);
+        float dinv;
+        chol_rows(S, lane, a, dinv);
+        const float x = chol_solve_rows(S, lane, a, dinv, (lane < NV) ? rhs : 0.0f);
+
+        if (phase == 0) {
+          qas = x;
+          if (DBG && A.dbg.qacc_smooth && lane < NV) A.dbg.qacc_smooth[(size_t)env * NV + lane] = qas;
+          // warm start (mjx solver.solve): cheaper of qacc_warmstart and qacc_smooth
+          float Ma_w = matvec_M(S, lane, ws);
+          rows_times(S, lane, nrow, ws, S.rjv);  // J*warm
+          float cs = 0.0f;
+          for (int r = lane; r < nrow; r += 32) {
+            float ja = S.rjv[r] - S.raref[r];
+            S.rjv[r] = ja;
+            cs += ja < 0.0f ? S.rD[r] * ja * ja : 0.0f;
+          }
+          float cost_w = 0.5f * warp_sum(cs) + 0.5f * warp_sum((lane < NV) ? (Ma_w - qfs) * (ws - qas) : 0.0f);
+          float Ma_s = matvec_M(S, lane, qas);
+          rows_times(S, lane, nrow, qas, S.rJaref);
+          cs = 0.0f;
+          for (int r = lane; r < nrow; r += 32) {
+            float ja = S.rJaref[r] - S.raref[r];
+            S.rJaref[r] = ja;
+            cs += ja < 0.0f ? S.rD[r] * ja * ja : 0.0f;
+          }
+          float cost_s = 0.5f * warp_sum(cs) + 0.5f * warp_sum((lane < NV) ? (Ma_s - qfs) * (qas - qas) : 0.0f);
+          const bool use_warm = cost_w < cost_s;
+          qacc = use_warm ? ws : qas;
+          Ma = use_warm ? Ma_w : Ma_s;
+          if (use_warm) for (int r = lane; r < nrow; r += 32) S.rJaref[r] = S.rjv[r];
+          __syncwarp();
+          cost = __int_as_float(0x7f800000);  // Context.create: cost = inf, prev_cost = 0
+          prev_cost = 0.0f;
+          update_constraint();
+          grad = Ma - qfs - qfc;
+          phase = 1;
+          continue;
+        }
+        if (phase == 2) { qacc_int = x; break; }
+
+        // ---- phase 1: x = Mgrad
+        search = -x;
+        // ---- line search (mjx solver._linesearch)
+        {
+          const float snorm = sqrtf(warp_sum((lane < NV) ? search * search : 0.0f));
+          const float gtol = C.tolerance * C.ls_tolerance * snorm * C.meaninertia * (float)max(1, C.nv);
+          const float mv = matvec_M(S, lane, search);
+          rows_times(S, lane, nrow, search, S.rjv);
+          const float qg0 = gauss;
+          const float qg1 = warp_sum((lane < NV) ? search * Ma : 0.0f) - warp_sum((lane < NV) ? search * qfs : 0.0f);
+          const float qg2 = 0.5f * warp_sum((lane < NV) ? search * mv : 0.0f);
+          float ja[NSTRIP], jv[NSTRIP], qa[NSTRIP], qb[NSTRIP], qc[NSTRIP];
+#pragma unroll
+          for (int s = 0; s < NSTRIP; s++) {
+            const int r = s * 32 + lane;
+            ja[s] = 1.0f; jv[s] = 0.0f; qa[s] = qb[s] = qc[s] = 0.0f;
+            if (r < nrow) {
+              const float D = S.rD[r];
+              ja[s] = S.rJaref[r]; jv[s] = S.rjv[r];
+              qa[s] = 0.5f * ja[s] * ja[s] * D; qb[s] = jv[s] * ja[s] * D; qc[s] = 0.5f * jv[s] * jv[s] * D;
+            }
+          }
+          auto point = [&](float alpha) {
+            float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f;
+#pragma unroll
+            for (int s = 0; s < NSTRIP; s++) {
+              const bool on = (ja[s] + alpha * jv[s]) < 0.0f;
+              p0 += on ? qa[s] : 0.0f; p1 += on ? qb[s] : 0.0f; p2 += on ? qc[s] : 0.0f;
+            }
+            p0 = qg0 + warp_sum(p0); p1 = qg1 + warp_sum(p1); p2 = qg2 + warp_sum(p2);
+            LSPoint pt;
+            pt.alpha = alpha;
+            pt.cost = alpha * alpha * p2 + alpha * p1 + p0;
+            pt.d0 = 2.0f * alpha * p2 + p1;
+            pt.d1 = 2.0f * p2 + (p2 == 0.0f ? MINVAL : 0.0f);
+            return pt;
+          };
+          const LSPoint p0 = point(0.0f);
+          LSPoint lo = point(p0.alpha - p0.d0 / p0.d1), hi;
+          if (lo.d0 < p0.d0) { hi = p0; } else { hi = lo; lo = p0; }
+          bool swap = true;
+          int ls_iter = 0;
+          while (true) {
+            bool ls_done = ls_iter >= C.ls_iterations;
+            ls_done |= !swap;
+            ls_done |= (lo.d0 < 0.0f) && (lo.d0 > -gtol);
+            ls_done |= (hi.d0 > 0.0f) && (hi.d0 < gtol);
+            if (ls_done) break;
+            const LSPoint lo_next = point(lo.alpha - lo.d0 / lo.d1);
+            const LSPoint hi_next = point(hi.alpha - hi.d0 / hi.d1);
+            const LSPoint mid = point(0.5f * (lo.alpha + hi.alpha));
+            const bool swap_lo_next = (lo.d0 > 0.0f) || (lo.d0 < lo_next.d0);
+            if (swap_lo_next) lo = lo_next;
+            const bool swap_lo_mid = (mid.d0 < 0.0f) && (lo.d0 < mid.d0);
+            if (swap_lo_mid) lo = mid;
+            const bool swap_hi_next = (hi.d0 < 0.0f) || (hi.d0 > hi_next.d0);
+            if (swap_hi_next) hi = hi_next;
+            const bool swap_hi_mid = (mid.d0 > 0.0f) && (hi.d0 > mid.d0);
+            if (swap_hi_mid) hi = mid;
+            swap = swap_lo_next || swap_lo_mid || swap_hi_next || swap_hi_mid;
+            ls_iter++;
+          }
+          const bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
+          const float alpha = lo.cost < hi.cost ? lo.alpha : hi.alpha;
+          if (improved) {
+            qacc += search * alpha;
+            Ma += mv * alpha;
+#pragma unroll
+            for (int s = 0; s < NSTRIP; s++) {
+              const int r = s * 32 + lane;
+              if (r < nrow) S.rJaref[r] = ja[s] + jv[s] * alpha;
+            }
+          }
+          __syncwarp();
+        }
+        update_constraint();
+        grad = Ma - qfs - qfc;
+        niter++;
+      }  // factor/solve loop
+
+      if (DBG) {
+        if (lane < NV) {
+          if (A.dbg.qacc) A.dbg.qacc[(size_t)env * NV + lane] = qacc;
+          if (A.dbg.qfrc_constraint) A.dbg.qfrc_constraint[(size_t)env * NV + lane] = qfc;
+        }
+        if (A.dbg.solver_niter && lane == 0) A.dbg.solver_niter[env] = niter;
+        for (int r = lane; r < nrow; r += 32) {
+          const int efc_row = S.rinfo[r] >> 16;
+          if (A.dbg.efc_force) A.dbg.efc_force[(size_t)env * C.nefc + efc_row] = S.rforce[r];
+          if (A.dbg.efc_active) A.dbg.efc_active[(size_t)env * C.nefc + efc_row] = 1 | (S.rJaref[r] < 0.0f ? 2 : 0);
+        }
+      }
+
+      // ---------------------------------------------------------------- touch sensors (mjx sensor.sensor_acc / engine_sensor.c mjSENS_TOUCH)
+      float sens[MJXB_MAXSENSOR];
+#pragma unroll
+      for (int s = 0; s < MJXB_MAXSENSOR; s++) sens[s] = 0.0f;
+      {
+        float nf = 0.0f;
+        int b1 = -1, b2 = -1;
+        if (lane < ncc) {
+          const int pr = S.cc_pair[lane], p = pr & 0xffff, rb = S.cc_row[lane];
+          const uint32_t w0 = C.pair_w0[p];
+          b1 = C.geom_body[w0 & 0xff]; b2 = C.geom_body[(w0 >> 8) & 0xff];
+          nf = S.rforce[rb];
+          if ((pr >> 20) > 1) nf = ((S.rforce[rb] + S.rforce[rb + 1]) + S.rforce[rb + 2]) + S.rforce[rb + 3];
+        }
+#pragma unroll
+        for (int s = 0; s < MJXB_MAXSENSOR; s++) {
+          float contrib = 0.0f;
+          if (s < C.nsensor && lane < ncc && nf > 0.0f) {
+            const int site = C.sensor_site[s], sb = C.site_body[site];
+            if (sb == b1 || sb == b2) {
+              float ray[3] = {S.cc_n[lane][0] * nf, S.cc_n[lane][1] * nf, S.cc_n[lane][2] * nf};
+              normalize3(ray);
+              if (sb == b2) { ray[0] = -ray[0]; ray[1] = -ray[1]; ray[2] = -ray[2]; }
+              float dp[3] = {S.cc_pos[lane][0] - S.site_xpos[site][0], S.cc_pos[lane][1] - S.site_xpos[site][1],
+                             S.cc_pos[lane][2] - S.site_xpos[site][2]};
+              const float* Rm = S.site_xmat[site];
+              float lp[3] = {Rm[0] * dp[0] + Rm[3] * dp[1] + Rm[6] * dp[2], Rm[1] * dp[0] + Rm[4] * dp[1] + Rm[7] * dp[2],
+                             Rm[2] * dp[0] + Rm[5] * dp[1] + Rm[8] * dp[2]};
+              float lv[3] = {Rm[0] * ray[0] + Rm[3] * ray[1] + Rm[6] * ray[2], Rm[1] * ray[0] + Rm[4] * ray[1] + Rm[7] * ray[2],
+                             Rm[2] * ray[0] + Rm[5] * ray[1] + Rm[8] * ray[2]};
+              if (ray_box(C.site_size[site], lp, lv) >= 0.0f) contrib = nf;
+            }
+          }
+          sens[s] = warp_sum(contrib);
+        }
+        if (DBG && A.dbg.sensordata && lane < C.nsensor) {
+          float sv = 0.0f;
+#pragma unroll
+          for (int s = 0; s < MJXB_MAXSENSOR; s++) if (s == lane) sv = sens[s];
+          A.dbg.sensordata[(size_t)env * C.nsensor + lane] = sv;
+        }
+      }
+
+      const float qacc_solver = qacc;  // qacc_warmstart <- solver qacc (mjx solver.solve tail)
+      if (!(fabsf(qacc_solver) < 3.0e38f)) status |= MJXB_STATUS_NAN;
+
+      // ---------------------------------------------------------------- integrate (mjx forward._advance)
+      if (integrate_pass) {
+        v = v + qacc_int * h;
+        __syncwarp();
+        S.vec[VQVEL][lane] = (lane < NV) ? v : 0.0f;
+        __syncwarp();
+        if (lane < C.nq) {
+          const int kind = C.qpos_kind[lane], ax = C.qpos_aux[lane];
+          if (kind == QK_HINGE || kind == QK_FREEPOS) {
+            q = q + h * S.vec[VQVEL][ax];
+          } else {
+            const int qa = ax & 0xff, comp = (ax >> 8) & 0xff, da = (ax >> 16) & 0xff;
+            float qq[4] = {S.vec[VQPOS][qa], S.vec[VQPOS][qa + 1], S.vec[VQPOS][qa + 2], S.vec[VQPOS][qa + 3]};
+            float w[3] = {S.vec[VQVEL][da], S.vec[VQVEL][da + 1], S.vec[VQVEL][da + 2]};
+            float nrm = normalize3(w), sn, cs;
+            sincosf(h * nrm * 0.5f, &sn, &cs);
+            float qr[4] = {cs, w[0] * sn, w[1] * sn, w[2] * sn}, qn[4];
+            quat_mul(qn, qq, qr);
+            float n2 = sqrtf(qn[0] * qn[0] + qn[1] * qn[1] + qn[2] * qn[2] + qn[3] * qn[3]);
+            float dn = n2 + (n2 == 0.0f ? 1e-6f : 0.0f);
+            q = (comp == 0 ? qn[0] : comp == 1 ? qn[1] : comp == 2 ? qn[2] : qn[3]) / dn;
+          }
+        }
+        tm = tm + h;
+      }
+      ws = qacc_solver;
+      if (!(fabsf(q) < 3.0e38f) || !(fabsf(v) < 3.0e38f)) status |= MJXB_STATUS_NAN;
+
+      // ---------------------------------------------------------------- env layer (src/envs.py) on the forward-pass frames
+      if (mode == MODE_ENV_STEP || mode == MODE_ENV_RESET) {
+        __syncwarp();
+        S.vec[VQPOS][lane] = q;       // post-integration qpos / qvel feed the observation
+        S.vec[VQVEL][lane] = (lane < NV) ? v : 0.0f;
+        __syncwarp();
+        const float bx = S.pelvis_pos[0], by = S.pelvis_pos[1], bz = S.pelvis_pos[2];
+        const float hx = S.head_pos[0], hy = S.head_pos[1];
+        const float qw = S.pelvis_quat[0], qx = S.pelvis_quat[1], qy = S.pelvis_quat[2], qz = S.pelvis_quat[3];
+        const float roll = atan2f(2.0f * (qw * qx + qy * qz), 1.0f - 2.0f * (qx * qx + qy * qy));
+        const float pitch = asinf(clampf(2.0f * (qw * qy - qz * qx), -1.0f, 1.0f));
+        const float yaw = atan2f(2.0f * (qw * qz + qx * qy), 1.0f - 2.0f * (qy * qy + qz * qz));
+        float sr = 0.0f, sl = 0.0f;
+#pragma unroll
+        for (int s = 0; s < MJXB_MAXSENSOR; s++) { if (s == cfg.touch_sensor_right_id) sr = sens[s]; if (s == cfg.touch_sensor_left_id) sl = sens[s]; }
+        const bool rcon = sr > 0.0f, lcon = sl > 0.0f;
+        const float new_stance = (rcon && lcon) ? 0.0f : (rcon && !lcon) ? 1.0f : (!rcon && lcon) ? 2.0f : 3.0f;
+        float flip, tx, ty, tz, close_count, stance, stance_time, last_pot, ep, dist_obs, dxo, dyo;
+        if (mode == MODE_ENV_STEP) {
+          flip = __shfl_sync(FULL, aux, 0); tx = __shfl_sync(FULL, aux, 1); ty = __shfl_sync(FULL, aux, 2); tz = __shfl_sync(FULL, aux, 3);
+          close_count = __shfl_sync(FULL, aux, 4); stance = __shfl_sync(FULL, aux, 5); stance_time = __shfl_sync(FULL, aux, 6);
+          last_pot = __shfl_sync(FULL, aux, 7); ep = __shfl_sync(FULL, aux, 8);
+          const float dx_p = tx - bx, dy_p = ty - by, dx_h = tx - hx, dy_h = ty - hy;
+          const float dist = fmaxf(sqrtf(dx_p * dx_p + dy_p * dy_p), sqrtf(dx_h * dx_h + dy_h * dy_h));
+          const float progress = (-dist / h - last_pot) * cfg.progress_weight;
+          const int nj = C.nv - 6;
+          const float pw = warp_sum((lane >= 6 && lane < NV) ? fabsf(qfrc_act * v) : 0.0f);
+          const float st2 = warp_sum((lane >= 6 && lane < NV) ? qfrc_act * qfrc_act : 0.0f);
+          const float energy = cfg.electricity_cost * (pw / (float)nj) + cfg.stall_torque_cost * (st2 / (float)nj);
+          const bool p_ok = (pitch > -0.087f) && (pitch < 0.174f), r_ok = (roll > -0.174f) && (roll < 0.174f);
+          const float posture = ((p_ok ? 0.0f : fabsf(pitch)) + (r_ok ? 0.0f : fabsf(roll))) * cfg.posture_penalty_weight;
+          const float tall = cfg.tall_bonus_weight * (bz > cfg.tall_height_threshold ? 1.0f : -1.0f);
+          const bool changed = new_stance != stance;
+          const float duration = tm - stance_time;
+          const float stance_reward = (changed && duration > 0.1f) ? cfg.stance_time_reward_weight * duration / h : 0.0f;
+          stance = changed ? new_stance : stance;
+          stance_time = changed ? tm : stance_time;
+          const bool is_close = dist < cfg.target_threshold;
+          close_count = is_close ? close_count + 1.0f : 0.0f;
+          const float target_bonus = is_close ? 2.0f : 0.0f;
+          if (close_count >= (float)cfg.stop_frames) { tx = bx + cfg.target_dist; ty = by; tz = bz; close_count = 0.0f; }
+          dxo = tx - bx; dyo = ty - by;
+          const float dx_h2 = tx - hx, dy_h2 = ty - hy;
+          dist_obs = fmaxf(sqrtf(dxo * dxo + dyo * dyo), sqrtf(dx_h2 * dx_h2 + dy_h2 * dy_h2));
+          last_pot = -dist_obs / h;
+          float reward = progress + target_bonus + stance_reward - energy + tall - posture - 0.0f;
+          ep = ep + 1.0f;
+          const bool fallen = bz < cfg.terminate_height;
+          out_term = fallen ? 1.0f : 0.0f;
+          out_trunc = (cfg.max_episode_steps > 0 && ep >= (float)cfg.max_episode_steps) ? 1.0f : 0.0f;
+          if (fallen) reward = reward + cfg.terminate_reward;
+          out_reward = reward;
+        } else {  // reset (src/envs.py:136-174)
+          flip = flip_r;
+          tx = bx + cfg.target_dist; ty = by; tz = bz;
+          dxo = tx - bx; dyo = ty - by;
+          const float dx_h = tx - hx, dy_h = ty - hy;
+          dist_obs = fmaxf(sqrtf(dxo * dxo + dyo * dyo), sqrtf(dx_h * dx_h + dy_h * dy_h));
+          last_pot = -dist_obs / h;
+          close_count = 0.0f; stance = new_stance; stance_time = tm; ep = 0.0f;
+        }
+        tgt_x = tx; tgt_y = ty; tgt_z = tz;
+        // aux' (src/envs.py:174,484)
+        aux = 0.0f;
+        if (lane == 0) aux = flip; if (lane == 1) aux = tx; if (lane == 2) aux = ty; if (lane == 3) aux = tz;
+        if (lane == 4) aux = close_count; if (lane == 5) aux = stance; if (lane == 6) aux = stance_time;
+        if (lane == 7) aux = last_pot; if (lane == 8) aux = ep;
+
+        const bool done_env = (mode == MODE_ENV_STEP) && (fmaxf(out_term, out_trunc) > 0.0f);
+        if (done_env && A.autoreset) {  // train_ppo.py:150-161 fused: re-run the pipeline in reset mode for this env
+          mode = MODE_ENV_RESET;
+          did_reset = 1;
+          continue;
+        }
+        // observation (src/envs.py:274-331): [height, rpy, qpos[7:], R^T v_lin, R^T v_ang, qvel[6:], tgt]
+        const float angle = atan2f(dyo, dxo) - yaw;
+        const float soft = dist_obs / (1.0f + fabsf(dist_obs));
+        const float tg0 = soft * sinf(angle), tg1 = soft * cosf(angle);
+        const float xx = qx * qx, yy = qy * qy, zz = qz * qz, xy = qx * qy, xz = qx * qz, yz = qy * qz, wx = qw * qx, wy = qw * qy, wz = qw * qz;
+        const float r00 = 1.0f - 2.0f * (yy + zz), r01 = 2.0f * (xy - wz), r02 = 2.0f * (xz + wy);
+        const float r10 = 2.0f * (xy + wz), r11 = 1.0f - 2.0f * (xx + zz), r12 = 2.0f * (yz - wx);
+        const float r20 = 2.0f * (xz - wy), r21 = 2.0f * (yz + wx), r22 = 1.0f - 2.0f * (xx + yy);
+        const int nqj = C.nq - 7, od = cfg.obs_dim;
+        for (int o = lane; o < od; o += 32) {
+          const int src = flip > 0.5f ? cfg.obs_perm[o] : o;
+          float val;
+          if (src == 0) val = bz;
+          else if (src == 1) val = roll;
+          else if (src == 2) val = pitch;
+          else if (src == 3) val = yaw;
+          else if (src < 4 + nqj) val = S.vec[VQPOS][7 + (src - 4)];
+          else if (src < 4 + nqj + 6) {
+            const int k = src - 4 - nqj, gsel = k / 3, c = k % 3;
+            const float lx = S.vec[VQVEL][3 * gsel], ly = S.vec[VQVEL][3 * gsel + 1], lz = S.vec[VQVEL][3 * gsel + 2];
+            val = c == 0 ? r00 * lx + r10 * ly + r20 * lz : c == 1 ? r01 * lx + r11 * ly + r21 * lz : r02 * lx + r12 * ly + r22 * lz;
+          } else if (src < 4 + nqj + C.nv) val = S.vec[VQVEL][6 + (src - 4 - nqj - 6)];
+          else val = (src == od - 2) ? tg0 : tg1;
+          if (flip > 0.5f) val *= cfg.obs_sign[o];
+          A.obs[(size_t)env * od + o] = val;
+        }
+      }
+      break;
+      }  // pass
+      (void)tgt_x; (void)tgt_y; (void)tgt_z;
+    }  // nsteps
+
+    // ------------------------------------------------------------------ store
+    if (A.mode == MODE_SPEED_TEST) {
+      if (lane == 0) A.pos[env] = q;
+    } else {
+      if (lane < C.nq) A.out.qpos[(size_t)env * C.nq + lane] = q;
+      if (lane < NV) { A.out.qvel[(size_t)env * NV + lane] = v; A.out.qacc_warmstart[(size_t)env * NV + lane] = ws; }
+      if (lane == 0) A.out.time[env] = tm;
+      if (A.mode == MODE_ENV_STEP || A.mode == MODE_ENV_RESET) {
+        if (lane < MJXB_AUX_DIM) A.out.aux[(size_t)env * MJXB_AUX_DIM + lane] = aux;
+      }
+      if (A.mode == MODE_ENV_STEP && lane == 0) {
+        A.reward[env] = out_reward; A.terminated[env] = out_term; A.truncated[env] = out_trunc;
+        if (A.reset_mask) A.reset_mask[env] = (uint8_t)did_reset;
+      }
+    }
+    if (A.status && lane == 0) A.status[env] = status;
+    __syncwarp();
+  }
+}
+
+}  // namespace mjxb

@@ -790,3 +790,49 @@ def emit_c_header() -> str:
         lines.append(f"  {ctype} {name}{dims};")
     lines += ["} mjxb_model_blob;", ""]
     return "\n".join(lines)
+
+
+# ----------------------------------------------------------------------------- (de)serialisation of the compiled dict
+def _to_jsonable(x):
+    if isinstance(x, np.ndarray):
+        return {"__nd__": x.tolist(), "dtype": str(x.dtype)}
+    if isinstance(x, (np.floating,)):
+        return float(x)
+    if isinstance(x, (np.integer,)):
+        return int(x)
+    if isinstance(x, dict):
+        return {k: _to_jsonable(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return [_to_jsonable(v) for v in x]
+    return x
+
+
+def _from_jsonable(x):
+    if isinstance(x, dict):
+        if "__nd__" in x:
+            return np.array(x["__nd__"], dtype=np.dtype(x["dtype"]))
+        return {k: _from_jsonable(v) for k, v in x.items()}
+    if isinstance(x, list):
+        return [_from_jsonable(v) for v in x]
+    return x
+
+
+def save_model(model: Dict[str, Any], path: str):
+    import json
+    with open(path, "w") as fh:
+        json.dump(_to_jsonable(model), fh)
+
+
+def load_model(path: str) -> Dict[str, Any]:
+    import json
+    with open(path) as fh:
+        m = _from_jsonable(json.load(fh))
+    for t in m["tendons"]:
+        t["wraps"] = [tuple(w) for w in t["wraps"]]
+    return m
+
+
+def builtin_model(name: str = "humanoid_mjx") -> Dict[str, Any]:
+    """Compiled constants shipped with the package (generated by tools/compile_models.py from the reference's XML)."""
+    import os
+    return load_model(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", f"{name}.json"))
