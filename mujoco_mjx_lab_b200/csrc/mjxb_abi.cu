@@ -40,8 +40,10 @@ struct mjxb_model {
   DevModel host;
   DevModel* dev = nullptr;
   PairParam* dev_pp = nullptr;
-  int device = 0, num_sms = 0, warps = 0;
-  size_t smem = 0;
+  int device = 0, num_sms = 0, warps = 0, warps_big = 0;
+  size_t smem = 0, smem_big = 0;
+  int* ovf = nullptr;   // [0] count, [1] done, [2..] env list
+  int ovf_cap = 0;
   Arena arena;
 };
 
@@ -161,7 +163,7 @@ int build_dev_model(const mjxb_model_blob& b, const mjxb_env_config* cfg, DevMod
     D.geom_rad[g] = b.geom_size[g][0]; D.geom_half[g] = b.geom_size[g][1];
     if (b.geom_type[g] == 0) { D.geom_rad[g] = 0.0f; D.geom_half[g] = 0.0f; }
   }
-  if (b.npair > MJXB_MAXPAIR || b.ncon > 0xffff || b.nefc > 0xffff) return MJXB_EUNSUPPORTED;
+  if (b.npair > MJXB_MAXPAIR || b.ncon > MAXCC_BIG || b.nefc > CAP_BIG) return MJXB_EUNSUPPORTED;
   for (int p = 0; p < b.npair; p++) {
     D.pair_w0[p] = (uint32_t)b.pair_g1[p] | ((uint32_t)b.pair_g2[p] << 8) | ((uint32_t)b.pair_kind[p] << 16) | ((uint32_t)b.pair_condim[p] << 24);
     D.pair_w1[p] = (uint32_t)b.pair_conadr[p] | ((uint32_t)b.pair_efcadr[p] << 16);
@@ -199,16 +201,36 @@ int build_dev_model(const mjxb_model_blob& b, const mjxb_env_config* cfg, DevMod
   return MJXB_OK;
 }
 
-int launch(const mjxb_model* m, const StepArgs& args, bool dbg, cudaStream_t stream) {
+using KMain = void (*)(const DevModel*, const PairParam*, StepArgs);
+
+int launch(const mjxb_model* mc, const StepArgs& args_in, bool dbg, cudaStream_t stream) {
+  mjxb_model* m = const_cast<mjxb_model*>(mc);  // the overflow list is library-owned scratch, grown on first use for a batch size
   int cur = 0;
   CU(cudaGetDevice(&cur));
   if (cur != m->device) CU(cudaSetDevice(m->device));
+  if (m->ovf_cap < args_in.n_env) {
+    if (m->ovf) { CU(cudaStreamSynchronize(stream)); CU(cudaFree(m->ovf)); m->ovf = nullptr; }
+    CU(cudaMalloc(&m->ovf, ((size_t)args_in.n_env + 2) * sizeof(int)));
+    CU(cudaMemsetAsync(m->ovf, 0, 2 * sizeof(int), stream));
+    m->ovf_cap = args_in.n_env;
+  }
+  StepArgs args = args_in;
+  args.ovf_count = m->ovf; args.ovf_done = m->ovf + 1; args.ovf_list = m->ovf + 2; args.consume_overflow = 0;
   const int warps = m->warps;
   int grid = (args.n_env + warps - 1) / warps;
   if (grid > m->num_sms) grid = m->num_sms;
-  if (dbg) mjxb_step_kernel<true><<<grid, warps * 32, m->smem, stream>>>(m->dev, m->dev_pp, args);
-  else mjxb_step_kernel<false><<<grid, warps * 32, m->smem, stream>>>(m->dev, m->dev_pp, args);
+  if (dbg) mjxb_step_kernel<true, CAP_MAIN, MAXCC_MAIN, WARPS_MAIN><<<grid, warps * 32, m->smem, stream>>>(m->dev, m->dev_pp, args);
+  else mjxb_step_kernel<false, CAP_MAIN, MAXCC_MAIN, WARPS_MAIN><<<grid, warps * 32, m->smem, stream>>>(m->dev, m->dev_pp, args);
   cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) {  // big-capacity pass over the envs the main pass could not hold (usually none: exits at once)
+    args.consume_overflow = 1;
+    const int wb = m->warps_big;
+    int gridb = m->num_sms;
+    if (gridb * wb > args.n_env) gridb = (args.n_env + wb - 1) / wb;
+    if (dbg) mjxb_step_kernel<true, CAP_BIG, MAXCC_BIG, WARPS_BIG><<<gridb, wb * 32, m->smem_big, stream>>>(m->dev, m->dev_pp, args);
+    else mjxb_step_kernel<false, CAP_BIG, MAXCC_BIG, WARPS_BIG><<<gridb, wb * 32, m->smem_big, stream>>>(m->dev, m->dev_pp, args);
+    e = cudaGetLastError();
+  }
   if (cur != m->device) cudaSetDevice(cur);
   if (e != cudaSuccess) return cuda_fail(e, "mjxb_step_kernel launch");
   return MJXB_OK;
@@ -266,13 +288,19 @@ int mjxb_model_create(const void* blob, size_t blob_bytes, const mjxb_env_config
   m->num_sms = prop.multiProcessorCount;
   const size_t model_bytes = (sizeof(DevModel) + 15) & ~size_t(15);
   const size_t avail = prop.sharedMemPerBlockOptin;
-  int warps = (int)((avail - model_bytes) / sizeof(WarpS));
-  if (warps > MAX_WARPS) warps = MAX_WARPS;
-  if (warps < 1) { delete m; cudaSetDevice(cur); return MJXB_EUNSUPPORTED; }
-  m->warps = warps;
-  m->smem = model_bytes + (size_t)warps * sizeof(WarpS);
-  CUX(cudaFuncSetAttribute(mjxb_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem));
-  CUX(cudaFuncSetAttribute(mjxb_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem));
+  using WSMain = WarpS<CAP_MAIN, MAXCC_MAIN>;
+  using WSBig = WarpS<CAP_BIG, MAXCC_BIG>;
+  int warps = (int)((avail - model_bytes) / sizeof(WSMain)), warps_big = (int)((avail - model_bytes) / sizeof(WSBig));
+  if (warps > WARPS_MAIN) warps = WARPS_MAIN;
+  if (warps_big > WARPS_BIG) warps_big = WARPS_BIG;
+  if (warps < 1 || warps_big < 1) { delete m; cudaSetDevice(cur); return MJXB_EUNSUPPORTED; }
+  m->warps = warps; m->warps_big = warps_big;
+  m->smem = model_bytes + (size_t)warps * sizeof(WSMain);
+  m->smem_big = model_bytes + (size_t)warps_big * sizeof(WSBig);
+  CUX(cudaFuncSetAttribute(mjxb_step_kernel<false, CAP_MAIN, MAXCC_MAIN, WARPS_MAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem));
+  CUX(cudaFuncSetAttribute(mjxb_step_kernel<true, CAP_MAIN, MAXCC_MAIN, WARPS_MAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem));
+  CUX(cudaFuncSetAttribute(mjxb_step_kernel<false, CAP_BIG, MAXCC_BIG, WARPS_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_big));
+  CUX(cudaFuncSetAttribute(mjxb_step_kernel<true, CAP_BIG, MAXCC_BIG, WARPS_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_big));
   CUX(cudaMalloc(&m->dev, sizeof(DevModel)));
   CUX(cudaMalloc(&m->dev_pp, sizeof(pp)));
   CUX(cudaMemcpy(m->dev, &m->host, sizeof(DevModel), cudaMemcpyHostToDevice));
@@ -288,6 +316,7 @@ void mjxb_model_destroy(mjxb_model* m) {
   arena_free(m->arena);
   if (m->dev) cudaFree(m->dev);
   if (m->dev_pp) cudaFree(m->dev_pp);
+  if (m->ovf) cudaFree(m->ovf);
   delete m;
 }
 
@@ -299,11 +328,11 @@ int mjxb_model_dims(const mjxb_model* m, int32_t dims[8]) {
   return MJXB_OK;
 }
 
-size_t mjxb_model_scratch_bytes(const mjxb_model* m) { (void)m; return 0; }
+size_t mjxb_model_scratch_bytes(const mjxb_model* m) { return m ? ((size_t)m->ovf_cap + 2) * sizeof(int) : 0; }
 
 int mjxb_launch_config(const mjxb_model* m, int32_t cfg[4]) {  // warps per CTA, dynamic smem bytes, SM count, sizeof(WarpS)
   if (!m || !cfg) return MJXB_EINVAL;
-  cfg[0] = m->warps; cfg[1] = (int32_t)m->smem; cfg[2] = m->num_sms; cfg[3] = (int32_t)sizeof(WarpS);
+  cfg[0] = m->warps; cfg[1] = (int32_t)m->smem; cfg[2] = m->num_sms; cfg[3] = (int32_t)sizeof(WarpS<CAP_MAIN, MAXCC_MAIN>);
   return MJXB_OK;
 }
 

@@ -20,10 +20,10 @@ namespace mjxb {
 
 constexpr int NV = 27;    // compile-time dof count: the register-resident factorisation is statically unrolled
 constexpr int NVP = 28;   // row stride (floats) of M and J: 16-byte aligned rows for 128-bit loads
-constexpr int CAP = 48;   // candidate constraint rows kept in shared memory per env
-constexpr int NSTRIP = (CAP + 31) / 32;
-constexpr int MAXCC = 24; // candidate contacts per env
-constexpr int MAX_WARPS = 12;  // warps (= envs in flight) per CTA; one CTA per SM, bounded by shared memory
+// Main instantiation: candidate constraint rows / candidate contacts held in shared memory per env. An env that needs
+// more is appended to an overflow list and re-run by the BIG instantiation (capacity >= every static row of the model).
+constexpr int CAP_MAIN = 48, MAXCC_MAIN = 24, WARPS_MAIN = 12;
+constexpr int CAP_BIG = 320, MAXCC_BIG = 176, WARPS_BIG = 3;
 constexpr unsigned FULL = 0xffffffffu;
 constexpr float MINVAL = 1e-15f;
 
@@ -76,12 +76,17 @@ struct StepArgs {
   int32_t* status;
   const float* vel;      // speed test
   float* pos;
+  int* ovf_count;        // overflow protocol (library-owned): main pass appends, big pass consumes and resets
+  int* ovf_list;
+  int* ovf_done;
+  int consume_overflow;  // 1: this launch iterates over ovf_list instead of 0..n_env
   mjxb_debug dbg;
 };
 
 // shared-memory vector slots (32 floats each)
 enum { VQPOS = 0, VQVEL, VCTRL, VX, VY, VTMP, NVEC };
 
+template <int CAP, int MAXCC>
 struct __align__(16) WarpS {
   alignas(16) float M[NV * NVP];
   union {
@@ -286,7 +291,8 @@ __device__ __forceinline__ float ray_box(const float* size, const float* pnt, co
 
 // ------------------------------------------------------------------------------------------- warp-level linear algebra on WarpS
 // y_i = sum_j M[i][j] x_j ; x is published through vec[VX]
-__device__ __forceinline__ float matvec_M(WarpS& S, int lane, float x) {
+template <class WS>
+__device__ __forceinline__ float matvec_M(WS& S, int lane, float x) {
   __syncwarp();
   S.vec[VX][lane] = (lane < NV) ? x : 0.0f;
   __syncwarp();
@@ -303,7 +309,8 @@ __device__ __forceinline__ float matvec_M(WarpS& S, int lane, float x) {
   return acc;
 }
 // out[r] = sum_d J[r][d] x_d for all rows (lane-per-row strips); x published through vec[VX]
-__device__ __forceinline__ void rows_times(WarpS& S, int lane, int nrow, float x, float* out /* smem [CAP] */) {
+template <class WS>
+__device__ __forceinline__ void rows_times(WS& S, int lane, int nrow, float x, float* out /* smem [CAP] */) {
   __syncwarp();
   S.vec[VX][lane] = (lane < NV) ? x : 0.0f;
   __syncwarp();
@@ -321,7 +328,8 @@ __device__ __forceinline__ void rows_times(WarpS& S, int lane, int nrow, float x
   __syncwarp();
 }
 // y_d = sum_r J[r][d] f_r
-__device__ __forceinline__ float rowsT_times(const WarpS& S, int lane, int nrow, const float* f /* smem [CAP] */) {
+template <class WS>
+__device__ __forceinline__ float rowsT_times(const WS& S, int lane, int nrow, const float* f /* smem [CAP] */) {
   float acc = 0.0f;
   if (lane < NVP) {
     for (int r = 0; r < nrow; r++) acc += S.J[r * NVP + lane] * f[r];
@@ -331,7 +339,8 @@ __device__ __forceinline__ float rowsT_times(const WarpS& S, int lane, int nrow,
 
 // In-register Cholesky of the SPD matrix whose row `lane` is a[0..NV) (lower part used). On return a[k] (k<lane) = L[lane][k],
 // dinv = 1 / L[lane][lane]. Column k is broadcast through S.col (double buffered): 27 SHFL + 27 STS + ~100 LDS.128.
-__device__ __forceinline__ void chol_rows(WarpS& S, int lane, float (&a)[NVP], float& dinv) {
+template <class WS>
+__device__ __forceinline__ void chol_rows(WS& S, int lane, float (&a)[NVP], float& dinv) {
   dinv = 1.0f;
 #pragma unroll
   for (int k = 0; k < NV; k++) {
@@ -357,7 +366,8 @@ __device__ __forceinline__ void chol_rows(WarpS& S, int lane, float (&a)[NVP], f
   }
 }
 // solve (L L^T) x = b with the factor from chol_rows; L rows are spilled to S.L for the backward pass
-__device__ __forceinline__ float chol_solve_rows(WarpS& S, int lane, const float (&a)[NVP], float dinv, float b) {
+template <class WS>
+__device__ __forceinline__ float chol_solve_rows(WS& S, int lane, const float (&a)[NVP], float dinv, float b) {
   float y = b;
 #pragma unroll
   for (int k = 0; k < NV; k++) {
@@ -384,8 +394,8 @@ __device__ __forceinline__ float chol_solve_rows(WarpS& S, int lane, const float
 struct LSPoint { float alpha, cost, d0, d1; };
 
 // ------------------------------------------------------------------------------------------- the kernel
-template <bool DBG>
-__global__ void __launch_bounds__(MAX_WARPS * 32, 1) mjxb_step_kernel(const DevModel* __restrict__ gmodel, const PairParam* __restrict__ pair_param,
+template <bool DBG, int CAP, int MAXCC, int MAXW>
+__global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel* __restrict__ gmodel, const PairParam* __restrict__ pair_param,
                                                             StepArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DevModel& C = *reinterpret_cast<DevModel*>(smem_raw);
@@ -396,17 +406,22 @@ __global__ void __launch_bounds__(MAX_WARPS * 32, 1) mjxb_step_kernel(const DevM
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  WarpS& S = *reinterpret_cast<WarpS*>(smem_raw + ((sizeof(DevModel) + 15) & ~size_t(15)) + (size_t)warp * sizeof(WarpS));
+  using WS = WarpS<CAP, MAXCC>;
+  constexpr int NSTRIP = (CAP + 31) / 32;
+  WS& S = *reinterpret_cast<WS*>(smem_raw + ((sizeof(DevModel) + 15) & ~size_t(15)) + (size_t)warp * sizeof(WS));
   const unsigned lt_mask = (1u << lane) - 1u;
   const float h = C.timestep;
   const mjxb_env_config& cfg = C.cfg;
   const int nbody = C.nbody;
 
-  for (int env = blockIdx.x * nwarp + warp; env < A.n_env; env += gridDim.x * nwarp) {
+  const int n_items = A.consume_overflow ? *reinterpret_cast<volatile int*>(A.ovf_count) : A.n_env;
+  for (int item = blockIdx.x * nwarp + warp; item < n_items; item += gridDim.x * nwarp) {
+    const int env = A.consume_overflow ? A.ovf_list[item] : item;
+    bool overflow = false;
     // ---------------------------------------------------------------- load state (lane d <-> qpos[d], qvel[d], ...)
     int mode = A.mode;
     float q = 0.0f, v = 0.0f, ws = 0.0f, ctrl = 0.0f, tm = 0.0f, aux = 0.0f, action = 0.0f;
-    int status = 0;
+    int status = A.consume_overflow ? MJXB_STATUS_ROW_SPILL : 0;
     if (mode == MODE_ENV_STEP || mode == MODE_PHYS_STEP || mode == MODE_FORWARD) {
       if (lane < C.nq) q = A.in.qpos[(size_t)env * C.nq + lane];
       if (lane < NV) { v = A.in.qvel[(size_t)env * NV + lane]; ws = A.in.qacc_warmstart[(size_t)env * NV + lane]; }
@@ -831,7 +846,7 @@ __global__ void __launch_bounds__(MAX_WARPS * 32, 1) mjxb_step_kernel(const DevM
           ncc += __popc(mk);
         }
       }
-      if (ncc > MAXCC) { status |= MJXB_STATUS_ROW_SPILL; ncc = MAXCC; }
+      if (ncc > MAXCC) { overflow = true; break; }
       __syncwarp();
 
       // ---------------------------------------------------------------- constraint rows: joint limits, tendon limits, contacts
@@ -880,12 +895,9 @@ __global__ void __launch_bounds__(MAX_WARPS * 32, 1) mjxb_step_kernel(const DevM
         int nfit = __popc(fm);  // candidates are dropped from the tail
         if (lane < ncc) S.cc_row[lane] = fits ? rbase : -1;
         int total = __shfl_sync(FULL, scan, 31);
-        if (nrow + total > CAP || nrow > CAP) {
-          status |= MJXB_STATUS_ROW_SPILL;
-          ncc = nfit;
-          nrow = min(nrow, CAP);
-          total = (nfit > 0) ? (__shfl_sync(FULL, scan, max(nfit - 1, 0))) : 0;
-        }
+        (void)nfit;
+        if (nrow + total > CAP) overflow = true;
+        if (overflow) { total = 0; ncc = 0; nrow = min(nrow, CAP); }  // unwound right after this block
         const int nrow_lim = nrow;
         nrow += total;
         __syncwarp();
@@ -988,6 +1000,7 @@ __global__ void __launch_bounds__(MAX_WARPS * 32, 1) mjxb_step_kernel(const DevM
         }
         __syncwarp();
       }
+      if (overflow) break;
 
       // ---------------------------------------------------------------- solve: one factor/solve code instance drives
       //   phase 0: qacc_smooth = M^-1 qfrc_smooth         (mjx smooth.factor_m/solve_m)
@@ -995,7 +1008,6 @@ __global__ void __launch_bounds__(MAX_WARPS * 32, 1) mjxb_step_kernel(const DevM
       //   phase 2: qacc'   = (M + h*damping)^-1 (qfrc_smooth + qfrc_constraint)   (mjx forward.implicit / euler)
       float qas = 0.0f, qacc = 0.0f, Ma = 0.0f, qfc = 0.0f, grad = 0.0f, search = 0.0f;
       float gauss = 0.0f, cost = 0.0f, prev_cost = 0.0f;
-      unsigned act0 = 0u, act1 = 0u;  // active mask of rows 0..31 / 32..63
       int niter = 0, phase = 0;
       const float scale = 1.0f / (C.meaninertia * (float)max(1, C.nv));
       float qacc_int = 0.0f;
@@ -1004,19 +1016,11 @@ __global__ void __launch_bounds__(MAX_WARPS * 32, 1) mjxb_step_kernel(const DevM
       // update_constraint (mjx solver._update_constraint) on the current Jaref/Ma/qacc
       auto update_constraint = [&]() {
         float cs = 0.0f;
-        act0 = 0u; act1 = 0u;
-#pragma unroll
-        for (int s = 0; s < NSTRIP; s++) {
-          const int r = s * 32 + lane;
-          bool active = false;
-          if (r < nrow) {
-            const float ja = S.rJaref[r], D = S.rD[r];
-            active = ja < 0.0f;
-            S.rforce[r] = active ? -D * ja : 0.0f;
-            cs += active ? D * ja * ja : 0.0f;
-          }
-          const unsigned mk = __ballot_sync(FULL, active);
-          if (s == 0) act0 = mk; else act1 = mk;
+        for (int r = lane; r < nrow; r += 32) {
+          const float ja = S.rJaref[r], D = S.rD[r];
+          const bool active = ja < 0.0f;
+          S.rforce[r] = active ? -D * ja : 0.0f;
+          cs += active ? D * ja * ja : 0.0f;
         }
         __syncwarp();
         qfc = rowsT_times(S, lane, nrow, S.rforce);
@@ -1058,8 +1062,7 @@ __global__ void __launch_bounds__(MAX_WARPS * 32, 1) mjxb_step_kernel(const DevM
         }
         if (phase == 1) {
           for (int r = 0; r < nrow; r++) {
-            const bool on = (r < 32) ? ((act0 >> r) & 1u) : ((act1 >> (r - 32)) & 1u);
-            if (!on) continue;
+            if (!(S.rJaref[r] < 0.0f)) continue;  // row inactive at the current iterate (warp-uniform)
             const float w = S.rD[r] * S.J[r * NVP + (lane < NVP ? lane : 0)];
             const float4* jr = reinterpret_cast<const float4*>(&S.J[r * NVP]);
 #pragma unroll
@@ -1385,7 +1388,17 @@ __global__ void __launch_bounds__(MAX_WARPS * 32, 1) mjxb_step_kernel(const DevM
       break;
       }  // pass
       (void)tgt_x; (void)tgt_y; (void)tgt_z;
+      if (overflow) break;
     }  // nsteps
+    if (overflow) {  // leave the env untouched; the big-capacity pass redoes it from its inputs
+      if (A.ovf_list != nullptr && !A.consume_overflow) {
+        if (lane == 0) { const int slot = atomicAdd(A.ovf_count, 1); A.ovf_list[slot] = env; }
+      } else if (A.status && lane == 0) {
+        A.status[env] = status | MJXB_STATUS_ROW_SPILL;
+      }
+      __syncwarp();
+      continue;
+    }
 
     // ------------------------------------------------------------------ store
     if (A.mode == MODE_SPEED_TEST) {
@@ -1404,6 +1417,14 @@ __global__ void __launch_bounds__(MAX_WARPS * 32, 1) mjxb_step_kernel(const DevM
     }
     if (A.status && lane == 0) A.status[env] = status;
     __syncwarp();
+  }
+  if (A.consume_overflow) {  // last CTA out resets the overflow counters for the next main launch
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const int t = atomicAdd(A.ovf_done, 1);
+      if (t == (int)gridDim.x - 1) { *A.ovf_count = 0; *A.ovf_done = 0; __threadfence(); }
+    }
   }
 }
 

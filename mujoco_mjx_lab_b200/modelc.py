@@ -576,7 +576,7 @@ def np_kinematics(model: Dict[str, Any], qpos: np.ndarray):
 
 def np_mass_matrix(model: Dict[str, Any], qpos: np.ndarray):
     """Dense joint-space inertia via per-body point Jacobians (independent of the CRB recursion the
-    oracle/kernels use): M = sum_b m_b Jp_b^T Jp_b + Jr_b^T I_b Jr_b + diag(armature)."""
+    CPU restatement and the kernels use): M = sum_b m_b Jp_b^T Jp_b + Jr_b^T I_b Jr_b + diag(armature)."""
     nb, nv = model["nbody"], model["nv"]
     xpos, xquat, xmat, xipos, xanchor, xaxis = np_kinematics(model, qpos)
     jacp, jacr = np_body_jacobians(model, xmat, xipos, xanchor, xaxis)
