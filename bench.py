@@ -1,0 +1,256 @@
+#!/usr/bin/env python
+"""bench.py -- humanoid physics env-steps/s on B200 (BASELINE.json metric), one JSON line on rank 0.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--envs E] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1], largest single-GPU size): humanoid_mjx.xml, 262144 envs per GPU, trajectory
+distribution B of SURVEY.md 8d (reset noise per src/envs.py:127-131,147, i.i.d. clip(N(0,1)) actions, auto-reset).
+A "step" is one pass of the hot path over the batch: v_step fused with the trainer's auto-reset (train_ppo.py:143-161).
+  value : env-steps/s summed over all ranks, inputs resident in HBM (actions / reset keys pre-generated on the device)
+  e2e   : the same step through the C ABI's host-buffer entry point (mjxb_step_autoreset_host): pinned host actions+keys
+          -> H2D -> kernel -> D2H of obs/reward/terminated/truncated, inside the timed region
+  roofline     : HBM roofline of the step kernel on its algorithmic bytes (1056 B / env-step)
+  roofline_fp32: the bound that actually applies (FP32 CUDA cores): counted algorithmic FLOPs / measured kernel time
+  cpu_baseline : the CPU oracle (restatement of the reference's MJX path; the reference itself cannot run here) on a
+                 bounded sample of the same workload, all host threads
+`--impl reference` times that CPU restatement as the reference arm (MJX / MuJoCo are not installable in this image).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "humanoid_env_steps_per_sec"
+UNIT = "env-steps/s"
+ALG_BYTES_PER_STEP = 1056          # state r/w 2*368 + action 84 + obs/reward/done 228 + key 8
+FP32_PEAK_TFLOPS = 74.4            # 148 SM x 128 lanes x 2 x 1.965 GHz (nominal)
+
+
+def algorithmic_flops(mean_newton_iters: float, mean_rows: float) -> float:
+    """Activity-aware counting model of SURVEY.md 8d: F = 70K + n_newton * (756 * n_act + 20K)."""
+    return 70e3 + mean_newton_iters * (756.0 * mean_rows + 20e3)
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.stop_flag = gpu_index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        reasons = set()
+        for r in self.rows:
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
+                "power_w_max": max(float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()) if self.rows else None,
+                "samples": len(self.rows), "reasons": sorted(reasons)}
+
+
+def cpu_reference_run(n_env: int, steps: int, warmup: int, seed: int = 42):
+    """The CPU restatement of the reference path (oracle/), all host threads, on a bounded sample of the bench workload."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    from oracle import oracle as O
+    O.build()
+    model = helpers.load()
+    orc = helpers.make_oracle(model, helpers.env_config())
+    rng = np.random.default_rng(seed)
+    st, _ = orc.env_reset(helpers.ppo_keys(seed, n_env))
+    for t in range(warmup):
+        st, *_ = orc.env_step(st, np.clip(rng.normal(size=(n_env, 21)), -1, 1), reset_keys=helpers.ppo_keys(1000 + t, n_env))
+    t0 = time.perf_counter()
+    for t in range(steps):
+        st, *_ = orc.env_step(st, np.clip(rng.normal(size=(n_env, 21)), -1, 1), reset_keys=helpers.ppo_keys(2000 + t, n_env))
+    dt = time.perf_counter() - t0
+    return n_env * steps / dt, dt, O.max_threads()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--envs", type=int, default=262144, help="envs per GPU (weak scaling)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-sample-envs", type=int, default=8192)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank, local_rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    config = {"workload": f"humanoid_mjx v_step+auto-reset, {args.envs} envs/GPU, trajectory distribution B (reset noise, clip(N(0,1)) actions)",
+              "model_xml": "models/humanoid_mjx.xml", "envs_per_gpu": args.envs, "solver": "Newton 10/20 pyramidal, implicitfast, dt=0.005",
+              "parallelism": f"env-sharded x{world}, no data-path collective",
+              "l2": "state+io per step = 0.28 GB > 126 MB L2 (inputs larger than L2)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        n = min(args.cpu_sample_envs, args.envs)
+        steps = max(1, min(args.steps, 8))
+        val, dt, threads = cpu_reference_run(n, steps, min(args.warmup, 3))
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 3),
+                "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                                 "sample": f"{n} envs x {steps} steps of the bench workload (CPU restatement of mjx.step + src/envs.py; "
+                                           "mujoco-mjx / jax are not installable in this image)"},
+                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    from mujoco_mjx_lab_b200 import _lib, mjx, modelc, parallel, training_utils
+    from mujoco_mjx_lab_b200.config import EnvConfig
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    if world > 1:
+        parallel.init("nccl")
+    model = modelc.builtin_model("humanoid_mjx")
+    cfg = EnvConfig(posture_penalty_weight=0.0, random_flip=True)        # effective PPO defaults (src/config.json)
+    m, sysm, q0, nq, nv, nu, single_reset, single_step, v_reset, v_step = training_utils.load_model_and_create_env("", cfg, model=model)
+    env_sys = v_step.sys
+    n = args.envs
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    nbuf = 8
+    acts = [torch.randn(n, nu, device=dev, generator=g).clamp_(-1, 1) for _ in range(nbuf)]
+    keys = [torch.randint(-2 ** 31, 2 ** 31 - 1, (n, 2), device=dev, dtype=torch.int32, generator=g) for _ in range(nbuf)]
+    state, obs = v_reset(torch.from_numpy(parallel.rank_keys(42, rank, n).view(np.int32)).to(dev))
+    # settle into the trajectory distribution (envs fall and get reset at different times) before measuring
+    for i in range(60):
+        state, obs, r, te, tr = v_step.autoreset(state, acts[i % nbuf], keys[i % nbuf], inplace=True)
+    for i in range(args.warmup):
+        state, obs, r, te, tr = v_step.autoreset(state, acts[i % nbuf], keys[i % nbuf], inplace=True)
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    parallel.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        state, obs, r, te, tr = v_step.autoreset(state, acts[i % nbuf], keys[i % nbuf], inplace=True)
+    e1.record()
+    torch.cuda.synchronize()
+    parallel.barrier()
+    ms_total = parallel.max_over_ranks(e0.elapsed_time(e1), dev)
+    if sampler:
+        sampler.stop_flag.set()
+        sampler.join(timeout=2)
+    ms_step = ms_total / args.steps
+    value = n * world * args.steps / (ms_total * 1e-3)
+    done_frac = float(torch.maximum(te, tr).mean())
+
+    # ---- end to end through the host-buffer ABI call (pinned host buffers; H2D + kernel + D2H timed)
+    L, h = _lib.lib(), env_sys.handle
+    pin = lambda *s, dt=torch.float32: torch.empty(*s, dtype=dt, pin_memory=True)
+    h_act = [pin(n, nu) for _ in range(2)]
+    for b in h_act:
+        b.copy_(acts[0].cpu())
+    h_keys = pin(n, 2, dt=torch.int32)
+    h_keys.copy_(keys[0].cpu())
+    h_obs, h_r, h_te, h_tr = pin(n, env_sys.obs_dim), pin(n), pin(n), pin(n)
+    d, aux = state
+    host_state = [np.ascontiguousarray(t.detach().cpu().numpy()) for t in (d.qpos, d.qvel, d.qacc_warmstart, d.time, aux)]  # keep alive
+    _lib.check(L.mjxb_state_set_host(h, n, *[a.ctypes.data for a in host_state]), "state_set_host")
+    e2e_steps = max(3, min(args.steps, 20))
+
+    def e2e_step(i):
+        _lib.check(L.mjxb_step_autoreset_host(h, n, h_act[i % 2].data_ptr(), h_keys.data_ptr(), h_obs.data_ptr(), h_r.data_ptr(),
+                                              h_te.data_ptr(), h_tr.data_ptr()), "step_autoreset_host")
+    for i in range(3):
+        e2e_step(i)
+    parallel.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    e2e_s = parallel.max_over_ranks(time.perf_counter() - t0, dev)
+    e2e_value = n * world * e2e_steps / e2e_s
+    h2d, d2h = n * (nu * 4 + 8), n * (env_sys.obs_dim + 3) * 4
+
+    # ---- solver statistics of the measured distribution (feeds the FLOP counting model) -- untimed
+    nstat = min(n, 65536)
+    dd = mjx.Data(d.qpos[:nstat], d.qvel[:nstat], d.qacc_warmstart[:nstat], d.time[:nstat], acts[0][:nstat])
+    _, dbg = mjx.forward(env_sys, dd, debug=True)
+    mean_iters = float(dbg["solver_niter"].float().mean())
+    mean_rows = float((dbg["efc_active"] & 1).sum(1).float().mean())
+    spill_frac = float(((dbg["status"] & 2) != 0).float().mean())
+    flops = algorithmic_flops(mean_iters, mean_rows)
+
+    if rank != 0:
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    kernel_ms = ms_step                                           # one step == one step-kernel launch (+ an empty overflow pass)
+    ach_gbs = ALG_BYTES_PER_STEP * n / (kernel_ms * 1e-3) / 1e9
+    ach_tflops = flops * n / (kernel_ms * 1e-3) / 1e12
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "api": "mjxb_step_autoreset_host (pinned host buffers)"},
+        "gpu_launches": 2 * args.steps,
+        "kernels": ["mjxb_step_kernel<false,48,24,12> (step)", "mjxb_step_kernel<false,320,176,3> (overflow re-run; exits at once when empty)"],
+        "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                     "traffic": None, "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 (of fallback)",
+                     "algorithmic_bytes_per_env_step": ALG_BYTES_PER_STEP, "kernel_ms": kernel_ms,
+                     "note": "the step is FP32-pipe/latency bound, ~16x under its HBM ceiling; see roofline_fp32"},
+        "roofline_fp32": {"bound": "fp32 CUDA cores", "achieved": ach_tflops, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
+                          "frac": ach_tflops / FP32_PEAK_TFLOPS, "flops_per_env_step": flops, "mean_newton_iters": mean_iters,
+                          "mean_candidate_rows": mean_rows, "peak_source": "nominal 148 SM x 128 lanes x 2 x 1.965 GHz"},
+        "workload_stats": {"done_frac_per_step": done_frac, "overflow_rerun_frac": spill_frac},
+        "published_reference_steps_per_sec": 72618, "x_published_reference": value / world / 72618.0,
+        "clocks": sampler.summary() if sampler else None,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        ncpu = min(args.cpu_sample_envs, n)
+        val, dt, threads = cpu_reference_run(ncpu, 4, 1)
+        line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"{ncpu} envs x 4 steps of the same workload, CPU oracle (float32 restatement of mjx.step + src/envs.py), {dt:.1f} s"}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()
