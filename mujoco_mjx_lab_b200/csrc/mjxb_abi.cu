@@ -89,6 +89,9 @@ int build_dev_model(const mjxb_model_blob& b, const mjxb_env_config* cfg, DevMod
   D.ntlimit = b.ntlimit; D.ncon1 = b.ncon1; D.solver = b.solver; D.iterations = b.iterations; D.ls_iterations = b.ls_iterations;
   D.damp_implicit = (b.integrator == 3) || (b.integrator == 0 && b.eulerdamp);
   D.maxdepth = b.maxdepth;
+  // exact line search whenever MJX's own search is run to convergence; the truncated settings keep MJX's iteration
+  D.ls_exact = (b.ls_iterations >= 10) ? 1 : 0;
+  if (getenv("MJXB_LS_ITERATIVE")) D.ls_exact = 0;
   D.timestep = b.timestep; D.tolerance = b.tolerance; D.ls_tolerance = b.ls_tolerance; D.meaninertia = b.meaninertia;
   for (int k = 0; k < 3; k++) D.gravity[k] = b.gravity[k];
   double tm = 0;
@@ -216,6 +219,7 @@ int launch(const mjxb_model* mc, const StepArgs& args_in, bool dbg, cudaStream_t
   }
   StepArgs args = args_in;
   args.ovf_count = m->ovf; args.ovf_done = m->ovf + 1; args.ovf_list = m->ovf + 2; args.consume_overflow = 0;
+  { const char* e = getenv("MJXB_LOCKSTEP"); args.lockstep = e ? atoi(e) : 1; }  // default on; MJXB_LOCKSTEP=0 disables (profiling aid)
   const int warps = m->warps;
   int grid = (args.n_env + warps - 1) / warps;
   if (grid > m->num_sms) grid = m->num_sms;

@@ -37,7 +37,7 @@ struct PairParam { float mu, invweight, solref[2], solimp[5]; };
 // Device copy of the model: the fields of mjxb_model_blob the kernels need, plus derived tables.
 struct DevModel {
   int nq, nv, nu, nbody, njnt, ngeom, nsite, ntendon, nsensor, npair, ncon, nefc, nlimit, ntlimit, ncon1;
-  int solver, iterations, ls_iterations, damp_implicit, maxdepth;
+  int solver, iterations, ls_iterations, damp_implicit, maxdepth, ls_exact;
   float timestep, gravity[3], tolerance, ls_tolerance, meaninertia, total_mass;
   int body_parent[MJXB_MAXBODY], body_depth[MJXB_MAXBODY], body_subtree_end[MJXB_MAXBODY], body_jntadr[MJXB_MAXBODY],
       body_jntnum[MJXB_MAXBODY];
@@ -63,7 +63,7 @@ struct DevModel {
   int site_body[MJXB_MAXSITE], sensor_site[MJXB_MAXSENSOR];
   float site_pos[MJXB_MAXSITE][3], site_quat[MJXB_MAXSITE][4], site_size[MJXB_MAXSITE][3];
   mjxb_env_config cfg;
-  int pad_[2];
+  int pad_[1];
 };
 
 struct StepArgs {
@@ -80,6 +80,7 @@ struct StepArgs {
   int* ovf_list;
   int* ovf_done;
   int consume_overflow;  // 1: this launch iterates over ovf_list instead of 0..n_env
+  int lockstep;          // CTA barriers keep the warps of an SM in the same code region (instruction-cache locality)
   mjxb_debug dbg;
 };
 
@@ -177,7 +178,7 @@ __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fm
 
 // ------------------------------------------------------------------------------------------- threefry / jax.random
 __device__ __forceinline__ uint32_t rotl32(uint32_t v, int r) { return (v << r) | (v >> (32 - r)); }
-__device__ __forceinline__ void threefry2x32(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t& o0, uint32_t& o1) {
+__device__ __noinline__ void threefry2x32(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t& o0, uint32_t& o1) {
   uint32_t ks0 = k0, ks1 = k1, ks2 = k0 ^ k1 ^ 0x1BD11BDAu;
   uint32_t x0 = c0 + ks0, x1 = c1 + ks1;
 #define MJXB_TF_R(r) { x0 += x1; x1 = rotl32(x1, r); x1 ^= x0; }
@@ -198,6 +199,10 @@ __device__ __forceinline__ float jax_uniform(uint32_t k0, uint32_t k1, uint32_t 
 }
 
 // ------------------------------------------------------------------------------------------- constraint impedance (mjx constraint._kbi)
+__device__ __noinline__ void kbi_general_power(float mid, float power, float x, float& ia, float& ib) {  // cold: solimp power not in {1, 2}
+  ia = (1.0f / powf(mid, power - 1.0f)) * powf(x, power);
+  ib = 1.0f - (1.0f / powf(1.0f - mid, power - 1.0f)) * powf(1.0f - x, power);
+}
 __device__ __forceinline__ void kbi(float timestep, const float* solref, const float* solimp, float pos, float& k, float& b, float& imp) {
   float timeconst = fmaxf(solref[0], 2.0f * timestep), dampratio = solref[1];
   float dmin = clampf(solimp[0], 1e-4f, 0.9999f), dmax = clampf(solimp[1], 1e-4f, 0.9999f);
@@ -210,7 +215,7 @@ __device__ __forceinline__ void kbi(float timestep, const float* solref, const f
   float ia, ib;
   if (power == 2.0f) { ia = (1.0f / mid) * (x * x); ib = 1.0f - (1.0f / (1.0f - mid)) * ((1.0f - x) * (1.0f - x)); }
   else if (power == 1.0f) { ia = x; ib = x; }
-  else { ia = (1.0f / powf(mid, power - 1.0f)) * powf(x, power); ib = 1.0f - (1.0f / powf(1.0f - mid, power - 1.0f)) * powf(1.0f - x, power); }
+  else { kbi_general_power(mid, power, x, ia, ib); }
   float y = x < mid ? ia : ib;
   imp = clampf(dmin + y * (dmax - dmin), dmin, dmax);
   if (x > 1.0f) imp = dmax;
@@ -271,7 +276,7 @@ __device__ __forceinline__ void make_tangents(const float* n, float* t1, float* 
   cross3(t2, n, b);
 }
 // nearest x >= 0 with pnt + x*vec on a face of the axis-aligned box `size`, else -1 (engine_ray.c ray_box / mjx ray._ray_box)
-__device__ __forceinline__ float ray_box(const float* size, const float* pnt, const float* vec) {
+__device__ __noinline__ float ray_box(const float* size, const float* pnt, const float* vec) {
   float best = -1.0f;
 #pragma unroll
   for (int i = 0; i < 3; i++) {
@@ -415,8 +420,14 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
   const int nbody = C.nbody;
 
   const int n_items = A.consume_overflow ? *reinterpret_cast<volatile int*>(A.ovf_count) : A.n_env;
-  for (int item = blockIdx.x * nwarp + warp; item < n_items; item += gridDim.x * nwarp) {
-    const int env = A.consume_overflow ? A.ovf_list[item] : item;
+  const int n_rounds = (n_items + gridDim.x * nwarp - 1) / (gridDim.x * nwarp);
+  for (int round = 0; round < n_rounds; round++) {
+    if (A.lockstep > 0 && (round % A.lockstep) == 0) __syncthreads();
+    const int item = (round * gridDim.x + blockIdx.x) * nwarp + warp;
+    // Warps without work in the last round (and envs that overflow the row tile) still run the whole pipeline -- on env 0 /
+    // on a truncated row set -- with every global store suppressed, so that all warps of the CTA reach the same barriers.
+    const bool valid = item < n_items;
+    const int env = valid ? (A.consume_overflow ? A.ovf_list[item] : item) : (A.consume_overflow ? A.ovf_list[0] : 0);
     bool overflow = false;
     // ---------------------------------------------------------------- load state (lane d <-> qpos[d], qvel[d], ...)
     int mode = A.mode;
@@ -452,7 +463,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
         v = (lane == 0) ? A.vel[env] : 0.0f;
         ws = 0.0f; ctrl = 0.0f; tm = 0.0f;
       }
-      for (int pass = 0; pass < 2; pass++) {  // pass 1 only for the fused auto-reset
+      for (int pass = 0; pass < 2; pass++) {  // pass 1 only for the fused auto-reset (no CTA barriers there)
       if (mode == MODE_ENV_RESET) {
         // ------------------------------------------------------------ single_reset state init (src/envs.py:117-131,147)
         uint32_t k1a, k1b, k2a, k2b, k3a, k3b, k4a, k4b;
@@ -846,7 +857,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
           ncc += __popc(mk);
         }
       }
-      if (ncc > MAXCC) { overflow = true; break; }
+      if (ncc > MAXCC) { overflow = true; ncc = MAXCC; }
       __syncwarp();
 
       // ---------------------------------------------------------------- constraint rows: joint limits, tendon limits, contacts
@@ -897,7 +908,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
         int total = __shfl_sync(FULL, scan, 31);
         (void)nfit;
         if (nrow + total > CAP) overflow = true;
-        if (overflow) { total = 0; ncc = 0; nrow = min(nrow, CAP); }  // unwound right after this block
+        if (overflow) { total = 0; ncc = 0; nrow = min(nrow, CAP); }  // results are discarded; keep the row set inside the tile
         const int nrow_lim = nrow;
         nrow += total;
         __syncwarp();
@@ -1000,7 +1011,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
         }
         __syncwarp();
       }
-      if (overflow) break;
+      if (A.lockstep > 0 && pass == 0) __syncthreads();  // all warps of the CTA enter the solver code together
 
       // ---------------------------------------------------------------- solve: one factor/solve code instance drives
       //   phase 0: qacc_smooth = M^-1 qfrc_smooth         (mjx smooth.factor_m/solve_m)
@@ -1030,6 +1041,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
       };
 
       while (true) {
+        asm volatile("" : "+r"(phase));  // keep `phase` opaque: the compiler otherwise clones the whole factor/solve body per phase
         if (phase == 1) {  // mjx solver.solve cond(): evaluated before paying for the next factorisation
           bool done;
           if (C.iterations == 1) {
@@ -1119,15 +1131,73 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
 
         // ---- phase 1: x = Mgrad
         search = -x;
-        // ---- line search (mjx solver._linesearch)
+        // ---- line search along `search`: minimise f(alpha) = gauss-quadratic + sum_r [Jaref_r + alpha jv_r < 0] D_r (Jaref_r + alpha jv_r)^2 / 2
         {
-          const float snorm = sqrtf(warp_sum((lane < NV) ? search * search : 0.0f));
-          const float gtol = C.tolerance * C.ls_tolerance * snorm * C.meaninertia * (float)max(1, C.nv);
           const float mv = matvec_M(S, lane, search);
           rows_times(S, lane, nrow, search, S.rjv);
           const float qg0 = gauss;
           const float qg1 = warp_sum((lane < NV) ? search * Ma : 0.0f) - warp_sum((lane < NV) ? search * qfs : 0.0f);
           const float qg2 = 0.5f * warp_sum((lane < NV) ? search * mv : 0.0f);
+          float alpha_step;   // step taken (0 = stay)
+          if (C.ls_exact) {
+            // Exact 1-D minimiser. f' is continuous, piecewise linear and non-decreasing with breakpoints
+            // alpha_r = -Jaref_r / jv_r; MJX's bracketed Newton iteration (solver._linesearch) converges to the same point.
+            // Lane r evaluates f'(alpha_r) over all rows (128-bit broadcast loads, no shuffles), two warp min/max reductions
+            // bracket the root, and the root of the linear piece inside the bracket is taken in closed form.
+            float* rls = S.rforce;   // per-row D*jv, published for the sweep (rforce is rebuilt by update_constraint)
+            float al[NSTRIP], gp[NSTRIP];
+            bool ok[NSTRIP];
+#pragma unroll
+            for (int st = 0; st < NSTRIP; st++) {
+              const int r = st * 32 + lane;
+              al[st] = 0.0f; gp[st] = 0.0f; ok[st] = false;
+              if (r < nrow) {
+                const float ja = S.rJaref[r], jv = S.rjv[r];
+                rls[r] = S.rD[r] * jv;
+                const float a_ = -ja / jv;
+                ok[st] = (jv != 0.0f) && (a_ > 0.0f) && (a_ < 3.0e38f);
+                al[st] = ok[st] ? a_ : 0.0f;
+              }
+            }
+            __syncwarp();
+            for (int r2 = 0; r2 < nrow; r2++) {
+              const float ja = S.rJaref[r2], jv = S.rjv[r2], dj = rls[r2];
+#pragma unroll
+              for (int st = 0; st < NSTRIP; st++) {
+                const float x = fmaf(al[st], jv, ja);
+                gp[st] += (x < 0.0f) ? dj * x : 0.0f;
+              }
+            }
+            unsigned lo_b = 0u, hi_b = 0x7f800000u;  // positive floats order like their bit patterns
+#pragma unroll
+            for (int st = 0; st < NSTRIP; st++) {
+              const float g_ = gp[st] + qg1 + 2.0f * al[st] * qg2;
+              if (ok[st] && g_ < 0.0f) lo_b = max(lo_b, __float_as_uint(al[st]));
+              if (ok[st] && !(g_ < 0.0f)) hi_b = min(hi_b, __float_as_uint(al[st]));
+            }
+            lo_b = __reduce_max_sync(FULL, lo_b);
+            hi_b = __reduce_min_sync(FULL, hi_b);
+            const float a_lo = __uint_as_float(lo_b), a_hi = __uint_as_float(hi_b);
+            const float a_mid = (hi_b == 0x7f800000u) ? (2.0f * a_lo + 1.0f) : 0.5f * (a_lo + a_hi);
+            float sa = 0.0f, sb = 0.0f, sc = 0.0f;  // quadratic piece on (a_lo, a_hi): f = C + alpha A + alpha^2 B
+            for (int r = lane; r < nrow; r += 32) {
+              const float ja = S.rJaref[r], jv = S.rjv[r], dj = rls[r];
+              const bool on = fmaf(a_mid, jv, ja) < 0.0f;
+              sa += on ? dj * ja : 0.0f;
+              sb += on ? dj * jv : 0.0f;
+              sc += on ? S.rD[r] * ja * ja : 0.0f;
+            }
+            const float Aq = qg1 + warp_sum(sa), Bq = qg2 + 0.5f * warp_sum(sb), Cq = qg0 + 0.5f * warp_sum(sc);
+            float a_star = (Bq > 0.0f) ? -Aq / (2.0f * Bq) : 0.0f;
+            a_star = fminf(fmaxf(a_star, a_lo), a_hi);
+            // MJX moves only if the evaluated cost improves on f(0) (solver._linesearch tail); this is what lets the outer loop's
+            // `improvement < tolerance` test fire once float32 can no longer resolve a decrease
+            const float cost_star = a_star * a_star * Bq + a_star * Aq + Cq;
+            alpha_step = (a_star > 0.0f && a_star < 3.0e38f && cost_star < cost) ? a_star : 0.0f;
+          } else {
+          // MJX's bracketed iteration, kept verbatim for truncated settings (lighten_solver: ls_iterations = 1)
+          const float snorm = sqrtf(warp_sum((lane < NV) ? search * search : 0.0f));
+          const float gtol = C.tolerance * C.ls_tolerance * snorm * C.meaninertia * (float)max(1, C.nv);
           float ja[NSTRIP], jv[NSTRIP], qa[NSTRIP], qb[NSTRIP], qc[NSTRIP];
 #pragma unroll
           for (int s = 0; s < NSTRIP; s++) {
@@ -1180,15 +1250,12 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
             ls_iter++;
           }
           const bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
-          const float alpha = lo.cost < hi.cost ? lo.alpha : hi.alpha;
-          if (improved) {
-            qacc += search * alpha;
-            Ma += mv * alpha;
-#pragma unroll
-            for (int s = 0; s < NSTRIP; s++) {
-              const int r = s * 32 + lane;
-              if (r < nrow) S.rJaref[r] = ja[s] + jv[s] * alpha;
-            }
+          alpha_step = improved ? (lo.cost < hi.cost ? lo.alpha : hi.alpha) : 0.0f;
+          }
+          if (alpha_step != 0.0f) {
+            qacc += search * alpha_step;
+            Ma += mv * alpha_step;
+            for (int r = lane; r < nrow; r += 32) S.rJaref[r] += S.rjv[r] * alpha_step;
           }
           __syncwarp();
         }
@@ -1197,6 +1264,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
         niter++;
       }  // factor/solve loop
 
+      if (A.lockstep > 0 && pass == 0) __syncthreads();  // ... and leave it together (early finishers would idle at the round barrier anyway)
       if (DBG) {
         if (lane < NV) {
           if (A.dbg.qacc) A.dbg.qacc[(size_t)env * NV + lane] = qacc;
@@ -1382,14 +1450,14 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
           } else if (src < 4 + nqj + C.nv) val = S.vec[VQVEL][6 + (src - 4 - nqj - 6)];
           else val = (src == od - 2) ? tg0 : tg1;
           if (flip > 0.5f) val *= cfg.obs_sign[o];
-          A.obs[(size_t)env * od + o] = val;
+          if (valid && !overflow) A.obs[(size_t)env * od + o] = val;
         }
       }
       break;
       }  // pass
       (void)tgt_x; (void)tgt_y; (void)tgt_z;
-      if (overflow) break;
     }  // nsteps
+    if (!valid) continue;
     if (overflow) {  // leave the env untouched; the big-capacity pass redoes it from its inputs
       if (A.ovf_list != nullptr && !A.consume_overflow) {
         if (lane == 0) { const int slot = atomicAdd(A.ovf_count, 1); A.ovf_list[slot] = env; }
