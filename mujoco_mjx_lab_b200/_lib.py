@@ -10,7 +10,7 @@ import subprocess
 from ._abi import DebugC, EnvConfigC, StateC
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmjxb.so")
+LIB_PATH = os.environ.get("MJXB_LIB", os.path.join(_HERE, "libmjxb.so"))  # MJXB_LIB: alternative build (tuning experiments)
 
 ERRORS = {0: "ok", -1: "invalid argument", -2: "bad model blob", -3: "CUDA error", -4: "no CUDA device (no CPU fallback)",
           -5: "unsupported model"}

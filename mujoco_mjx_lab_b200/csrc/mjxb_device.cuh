@@ -22,7 +22,12 @@ constexpr int NV = 27;    // compile-time dof count: the register-resident facto
 constexpr int NVP = 28;   // row stride (floats) of M and J: 16-byte aligned rows for 128-bit loads
 // Main instantiation: candidate constraint rows / candidate contacts held in shared memory per env. An env that needs
 // more is appended to an overflow list and re-run by the BIG instantiation (capacity >= every static row of the model).
-constexpr int CAP_MAIN = 48, MAXCC_MAIN = 24, WARPS_MAIN = 12;
+#ifndef MJXB_CAP_MAIN
+#define MJXB_CAP_MAIN 32
+#define MJXB_MAXCC_MAIN 16
+#define MJXB_WARPS_MAIN 16
+#endif
+constexpr int CAP_MAIN = MJXB_CAP_MAIN, MAXCC_MAIN = MJXB_MAXCC_MAIN, WARPS_MAIN = MJXB_WARPS_MAIN;
 constexpr int CAP_BIG = 320, MAXCC_BIG = 176, WARPS_BIG = 3;
 constexpr unsigned FULL = 0xffffffffu;
 constexpr float MINVAL = 1e-15f;
@@ -81,6 +86,7 @@ struct StepArgs {
   int* ovf_done;
   int consume_overflow;  // 1: this launch iterates over ovf_list instead of 0..n_env
   int lockstep;          // CTA barriers keep the warps of an SM in the same code region (instruction-cache locality)
+  int lockstep_group;    // warps per barrier group (0 = the whole CTA)
   mjxb_debug dbg;
 };
 
@@ -398,6 +404,15 @@ __device__ __forceinline__ float chol_solve_rows(WS& S, int lane, const float (&
 
 struct LSPoint { float alpha, cost, d0, d1; };
 
+// barrier over a group of `g` consecutive warps (named barrier 1 + group index); g <= 0 or g >= CTA: the whole CTA
+__device__ __forceinline__ void group_sync(int warp, int g) {
+  const int nwarp = blockDim.x >> 5;
+  if (g <= 0 || g >= nwarp) { __syncthreads(); return; }
+  const int grp = warp / g;
+  const int cnt = min(g, nwarp - grp * g) * 32;
+  asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(cnt) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------- the kernel
 template <bool DBG, int CAP, int MAXCC, int MAXW>
 __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel* __restrict__ gmodel, const PairParam* __restrict__ pair_param,
@@ -422,7 +437,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
   const int n_items = A.consume_overflow ? *reinterpret_cast<volatile int*>(A.ovf_count) : A.n_env;
   const int n_rounds = (n_items + gridDim.x * nwarp - 1) / (gridDim.x * nwarp);
   for (int round = 0; round < n_rounds; round++) {
-    if (A.lockstep > 0 && (round % A.lockstep) == 0) __syncthreads();
+    if (A.lockstep > 0) group_sync(warp, A.lockstep_group);
     const int item = (round * gridDim.x + blockIdx.x) * nwarp + warp;
     // Warps without work in the last round (and envs that overflow the row tile) still run the whole pipeline -- on env 0 /
     // on a truncated row set -- with every global store suppressed, so that all warps of the CTA reach the same barriers.
@@ -1011,7 +1026,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
         }
         __syncwarp();
       }
-      if (A.lockstep > 0 && pass == 0) __syncthreads();  // all warps of the CTA enter the solver code together
+      if (A.lockstep > 0 && pass == 0) group_sync(warp, A.lockstep_group);  // all warps of the group enter the solver code together
 
       // ---------------------------------------------------------------- solve: one factor/solve code instance drives
       //   phase 0: qacc_smooth = M^-1 qfrc_smooth         (mjx smooth.factor_m/solve_m)
@@ -1264,7 +1279,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
         niter++;
       }  // factor/solve loop
 
-      if (A.lockstep > 0 && pass == 0) __syncthreads();  // ... and leave it together (early finishers would idle at the round barrier anyway)
+      if (A.lockstep > 0 && A.lockstep != 2 && pass == 0) group_sync(warp, A.lockstep_group);  // ... and leave it together (early finishers would idle at the round barrier anyway)
       if (DBG) {
         if (lane < NV) {
           if (A.dbg.qacc) A.dbg.qacc[(size_t)env * NV + lane] = qacc;

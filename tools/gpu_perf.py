@@ -54,3 +54,7 @@ for n in sizes:
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         print(f"          speed_test iters={it:3d}: {ms:8.3f} ms  {n * it / ms * 1e3:12.0f} steps/s")
+    hist = torch.bincount(out["solver_niter"].flatten().long(), minlength=11).float()
+    print("          niter histogram %:", [round(float(x) * 100 / hist.sum().item(), 1) for x in hist])
+    rows_hist = torch.bincount((cand / 4).long().clamp(max=12), minlength=13).float()
+    print("          cand rows/4 histogram %:", [round(float(x) * 100 / rows_hist.sum().item(), 1) for x in rows_hist])
