@@ -1069,6 +1069,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
           }
           if (done) {
             if (!integrate_pass) break;
+            if (!C.damp_implicit) { qacc_int = qacc; break; }  // plain Euler without eulerdamp integrates the solver's qacc
             phase = 2;
           }
         }

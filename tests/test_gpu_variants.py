@@ -1,0 +1,45 @@
+"""Other models / solver settings through the same kernels: humanoid.xml (Euler + eulerdamp, Newton 100/50, all-pairs
+collisions: 159 pairs / 303 rows, plane-sphere and sphere-sphere primitives) and lighten_solver (1 iteration, MJX's truncated
+line search kept verbatim)."""
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from mujoco_mjx_lab_b200 import mjx
+from test_gpu_parity import N, T, assert_f32_equivalent, rel
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare(model, kind, seed, n=256, tol_floor=1e-4):
+    orc = helpers.make_oracle(model)
+    sysm = mjx.put_model(model)
+    q, v, w, c = helpers.make_states(model, n, seed, kind)
+    ref = orc.physics_step(q, v, w, None, c, prec="f64", debug=("qacc", "con_dist", "efc_active", "solver_niter"))
+    r32 = orc.physics_step(q, v, w, None, c, prec="f32", debug=("qacc",))
+    d = mjx.Data(T(q), T(v), T(w), torch.zeros(n, device="cuda"), T(c))
+    _, dbg = mjx.forward(sysm, d, debug=True)
+    nd = mjx.step(sysm, d)
+    assert np.abs(N(dbg["con_dist"]) - ref["con_dist"]).max() < 2e-6
+    cand_g, cand_r = dbg["efc_active"].cpu().numpy() & 1, ref["efc_active"] & 1
+    ok = (cand_g == cand_r).all(axis=1)
+    assert ok.mean() > 0.97
+    assert_f32_equivalent(rel(N(dbg["qacc"]), ref["qacc"])[ok].max(axis=1), rel(r32["qacc"], ref["qacc"])[ok].max(axis=1), tol_floor, "qacc")
+    assert_f32_equivalent(np.abs(N(nd.qvel) - ref["qvel"])[ok].max(axis=1), np.abs(r32["qvel"] - ref["qvel"])[ok].max(axis=1), 1e-5, "qvel")
+    assert_f32_equivalent(np.abs(N(nd.qpos) - ref["qpos"])[ok].max(axis=1), np.abs(r32["qpos"] - ref["qpos"])[ok].max(axis=1), 1e-6, "qpos")
+    return dbg, ref
+
+
+@pytest.mark.parametrize("kind", ["lean", "tumble"])
+def test_humanoid_xml(kind):
+    model = helpers.load("humanoid")
+    dbg, ref = _compare(model, kind, 400)
+    assert (ref["efc_active"] & 1).sum(axis=1).max() > 20
+
+
+def test_lighten_solver_iterative_linesearch():
+    """reference src/training_utils.py:95-98: iterations = ls_iterations = 1 (the APG configuration)."""
+    model = helpers.load(overrides=dict(iterations=1, ls_iterations=1))
+    dbg, ref = _compare(model, "lean", 500, tol_floor=1e-3)
+    assert int(dbg["solver_niter"].max()) == 1 and int(ref["solver_niter"].max()) == 1
