@@ -105,6 +105,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-sample-envs", type=int, default=8192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ppo", action="store_true")
+    ap.add_argument("--ppo-large", action="store_true", help="also time config 5 (65536 envs/GPU PPO iteration)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank, local_rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -214,6 +216,16 @@ def main():
     spill_frac = float(((dbg["status"] & 2) != 0).float().mean())
     flops = algorithmic_flops(mean_iters, mean_rows)
 
+    # ---- PPO iteration time (the second half of BASELINE.json's metric): the caller of the hot path, reference train_ppo.py
+    ppo = {}
+    if not args.no_ppo:
+        from mujoco_mjx_lab_b200 import ppo as ppo_mod
+        del acts, keys, state, obs
+        torch.cuda.empty_cache()
+        n3 = max(1024 // world, 16)                                  # config 3: 1024 envs total x 256 steps, sharded
+        ppo["config3"] = ppo_mod.time_ppo(n3, 256, iters=5, warmup=3, minibatch_size=65536, model=model)
+        if args.ppo_large:                                           # config 5: 65536 envs per GPU, NCCL gradient all-reduce
+            ppo["config5"] = ppo_mod.time_ppo(65536, 256, iters=2, warmup=1, minibatch_size=65536, model=model)
     if rank != 0:
         return
     peaks = {}
@@ -243,6 +255,7 @@ def main():
         "workload_stats": {"done_frac_per_step": done_frac, "overflow_rerun_frac": spill_frac},
         "published_reference_steps_per_sec": 72618, "x_published_reference": value / world / 72618.0,
         "clocks": sampler.summary() if sampler else None,
+        "ppo_iter": ppo,
     }
     if not args.no_cpu_baseline and world == 1:
         ncpu = min(args.cpu_sample_envs, n)

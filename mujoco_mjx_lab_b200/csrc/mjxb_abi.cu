@@ -224,16 +224,23 @@ int launch(const mjxb_model* mc, const StepArgs& args_in, bool dbg, cudaStream_t
   const int warps = m->warps;
   int grid = (args.n_env + warps - 1) / warps;
   if (grid > m->num_sms) grid = m->num_sms;
-  if (dbg) mjxb_step_kernel<true, CAP_MAIN, MAXCC_MAIN, WARPS_MAIN><<<grid, warps * 32, m->smem, stream>>>(m->dev, m->dev_pp, args);
-  else mjxb_step_kernel<false, CAP_MAIN, MAXCC_MAIN, WARPS_MAIN><<<grid, warps * 32, m->smem, stream>>>(m->dev, m->dev_pp, args);
+  const bool ls = m->host.ls_exact != 0;
+#define MJXB_LAUNCH(CAPv, CCv, Wv, G, B, SM)                                                                                   \
+  do {                                                                                                                        \
+    if (dbg && ls) mjxb_step_kernel<true, CAPv, CCv, Wv, true><<<G, B, SM, stream>>>(m->dev, m->dev_pp, args);                  \
+    else if (dbg) mjxb_step_kernel<true, CAPv, CCv, Wv, false><<<G, B, SM, stream>>>(m->dev, m->dev_pp, args);                  \
+    else if (ls) mjxb_step_kernel<false, CAPv, CCv, Wv, true><<<G, B, SM, stream>>>(m->dev, m->dev_pp, args);                   \
+    else mjxb_step_kernel<false, CAPv, CCv, Wv, false><<<G, B, SM, stream>>>(m->dev, m->dev_pp, args);                          \
+  } while (0)
+  MJXB_LAUNCH(CAP_MAIN, MAXCC_MAIN, WARPS_MAIN, grid, warps * 32, m->smem);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) {  // big-capacity pass over the envs the main pass could not hold (usually none: exits at once)
     args.consume_overflow = 1;
     const int wb = m->warps_big;
     int gridb = m->num_sms;
     if (gridb * wb > args.n_env) gridb = (args.n_env + wb - 1) / wb;
-    if (dbg) mjxb_step_kernel<true, CAP_BIG, MAXCC_BIG, WARPS_BIG><<<gridb, wb * 32, m->smem_big, stream>>>(m->dev, m->dev_pp, args);
-    else mjxb_step_kernel<false, CAP_BIG, MAXCC_BIG, WARPS_BIG><<<gridb, wb * 32, m->smem_big, stream>>>(m->dev, m->dev_pp, args);
+    MJXB_LAUNCH(CAP_BIG, MAXCC_BIG, WARPS_BIG, gridb, wb * 32, m->smem_big);
+#undef MJXB_LAUNCH
     e = cudaGetLastError();
   }
   if (cur != m->device) cudaSetDevice(cur);
@@ -302,10 +309,11 @@ int mjxb_model_create(const void* blob, size_t blob_bytes, const mjxb_env_config
   m->warps = warps; m->warps_big = warps_big;
   m->smem = model_bytes + (size_t)warps * sizeof(WSMain);
   m->smem_big = model_bytes + (size_t)warps_big * sizeof(WSBig);
-  CUX(cudaFuncSetAttribute(mjxb_step_kernel<false, CAP_MAIN, MAXCC_MAIN, WARPS_MAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem));
-  CUX(cudaFuncSetAttribute(mjxb_step_kernel<true, CAP_MAIN, MAXCC_MAIN, WARPS_MAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem));
-  CUX(cudaFuncSetAttribute(mjxb_step_kernel<false, CAP_BIG, MAXCC_BIG, WARPS_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_big));
-  CUX(cudaFuncSetAttribute(mjxb_step_kernel<true, CAP_BIG, MAXCC_BIG, WARPS_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_big));
+#define MJXB_SMEM_ATTR(DBGv, LSv)                                                                                                         \
+  CUX(cudaFuncSetAttribute(mjxb_step_kernel<DBGv, CAP_MAIN, MAXCC_MAIN, WARPS_MAIN, LSv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem)); \
+  CUX(cudaFuncSetAttribute(mjxb_step_kernel<DBGv, CAP_BIG, MAXCC_BIG, WARPS_BIG, LSv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_big));
+  MJXB_SMEM_ATTR(false, true) MJXB_SMEM_ATTR(true, true) MJXB_SMEM_ATTR(false, false) MJXB_SMEM_ATTR(true, false)
+#undef MJXB_SMEM_ATTR
   CUX(cudaMalloc(&m->dev, sizeof(DevModel)));
   CUX(cudaMalloc(&m->dev_pp, sizeof(pp)));
   CUX(cudaMemcpy(m->dev, &m->host, sizeof(DevModel), cudaMemcpyHostToDevice));

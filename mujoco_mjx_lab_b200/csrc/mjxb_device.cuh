@@ -414,7 +414,7 @@ __device__ __forceinline__ void group_sync(int warp, int g) {
 }
 
 // ------------------------------------------------------------------------------------------- the kernel
-template <bool DBG, int CAP, int MAXCC, int MAXW>
+template <bool DBG, int CAP, int MAXCC, int MAXW, bool LS_EXACT>
 __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel* __restrict__ gmodel, const PairParam* __restrict__ pair_param,
                                                             StepArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1155,7 +1155,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
           const float qg1 = warp_sum((lane < NV) ? search * Ma : 0.0f) - warp_sum((lane < NV) ? search * qfs : 0.0f);
           const float qg2 = 0.5f * warp_sum((lane < NV) ? search * mv : 0.0f);
           float alpha_step;   // step taken (0 = stay)
-          if (C.ls_exact) {
+          if (LS_EXACT) {
             // Exact 1-D minimiser. f' is continuous, piecewise linear and non-decreasing with breakpoints
             // alpha_r = -Jaref_r / jv_r; MJX's bracketed Newton iteration (solver._linesearch) converges to the same point.
             // Lane r evaluates f'(alpha_r) over all rows (128-bit broadcast loads, no shuffles), two warp min/max reductions

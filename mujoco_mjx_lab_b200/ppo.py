@@ -1,0 +1,272 @@
+"""PPO iteration driver for the B200 env path: the *caller* of the hot path (reference train_ppo.py:41-463), kept to what the
+timing of BASELINE.json configs 3 and 5 needs: rollout (policy -> fused step+auto-reset), RMS observation statistics, GAE,
+clipped-PPO updates with two Adam optimisers, and -- when envs are sharded over several GPUs -- NCCL all-reduce of the
+gradients and of the RMS statistics.  Networks and optimiser stay in the host framework (torch here, JAX in the
+reference): pure library GEMMs, not part of the kernel scope.
+
+Same hyper-parameters and update rule as the reference:
+  policy / value MLP 3x256 tanh, Glorot-normal init, state-independent log_std (reference src/networks.py:21-131)
+  rollout: pre-step obs stored, reward/terminated/truncated of the step, reset obs carried (train_ppo.py:128-169)
+  GAE with terminate/truncate distinction (train_ppo.py:171-202), advantage normalised per minibatch (:209)
+  clipped objective + entropy bonus, separate value MSE, Adam(lr_policy) / Adam(lr_value) (:204-252)
+The rollout of `rollout_length` steps is captured once in a CUDA graph (policy GEMMs, sampling, the step kernel, trajectory
+stores) and replayed per iteration: the host is out of the T-loop.
+"""
+from __future__ import annotations
+
+import math
+import time
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import parallel
+from .config import PPOConfig
+from .mjx import Data
+
+
+def _mlp_params(in_dim: int, specs, out_dim: Optional[int], gen: torch.Generator, device):
+    dims = [in_dim] + [int(h) for h, _ in specs] + ([out_dim] if out_dim is not None else [])
+    params = []
+    for a, b in zip(dims[:-1], dims[1:]):
+        w = torch.randn(a, b, generator=gen, device=device) * math.sqrt(2.0 / (a + b))      # reference src/networks.py:44-47
+        params += [w.requires_grad_(), torch.zeros(b, device=device, requires_grad=True)]
+    return params
+
+
+def _mlp_apply(params, x, n_hidden: int):
+    for i in range(0, len(params), 2):
+        x = torch.addmm(params[i + 1], x, params[i])
+        if i // 2 < n_hidden:
+            x = torch.tanh(x)
+    return x
+
+
+def gaussian_logprob(mean, log_std, action):  # reference train_ppo.py:121-126
+    var = torch.exp(2.0 * log_std)
+    return -0.5 * torch.sum((action - mean) ** 2 / var + 2.0 * log_std + math.log(2.0 * math.pi), dim=-1)
+
+
+@dataclass
+class RMS:  # reference src/training_utils.py:20-56
+    mean: torch.Tensor
+    var: torch.Tensor
+    count: torch.Tensor
+
+    @classmethod
+    def create(cls, dim, device):
+        return cls(torch.zeros(dim, device=device), torch.ones(dim, device=device), torch.tensor(1e-4, device=device))
+
+    def update(self, x: torch.Tensor, world: int):
+        """Welford merge of the batch moments; with sharded envs the batch moments are all-reduced first."""
+        n = torch.tensor(float(x.shape[0]), device=x.device)
+        s1, s2 = x.sum(0), (x * x).sum(0)
+        if world > 1:
+            packed = torch.cat([s1, s2, n.reshape(1)])
+            dist.all_reduce(packed)
+            s1, s2, n = packed[: x.shape[1]], packed[x.shape[1]: 2 * x.shape[1]], packed[-1]
+        b_mean = s1 / n
+        b_var = s2 / n - b_mean * b_mean
+        delta = b_mean - self.mean
+        tot = self.count + n
+        self.mean = self.mean + delta * n / tot
+        m_a, m_b = self.var * self.count, b_var * n
+        self.var = (m_a + m_b + delta * delta * self.count * n / tot) / tot
+        self.count = tot
+
+    def normalize(self, x):
+        return torch.clamp((x - self.mean) / torch.sqrt(self.var + 1e-8), -10.0, 10.0)
+
+
+class PPOTrainer:
+    def __init__(self, cfg: PPOConfig, v_reset, v_step, num_envs_local: int, seed: int = 42, use_cuda_graph: bool = True):
+        self.cfg, self.v_reset, self.v_step = cfg, v_reset, v_step
+        self.sys = v_step.sys
+        self.dev = self.sys.device
+        self.n, self.T = num_envs_local, cfg.rollout_length
+        self.rank, _, self.world = parallel.dist_env()
+        if self.world > 1 and not dist.is_initialized():
+            parallel.init("nccl")
+        od, nu = self.sys.obs_dim, self.sys.nu
+        gen = torch.Generator(device=self.dev).manual_seed(seed)           # same init on every rank
+        self.nh_p, self.nh_v = len(cfg.policy_hidden_layer_specs), len(cfg.value_hidden_layer_specs)
+        self.policy = _mlp_params(od, cfg.policy_hidden_layer_specs, nu, gen, self.dev)
+        self.log_std = torch.full((nu,), float(cfg.log_std_init), device=self.dev, requires_grad=True)
+        self.value = _mlp_params(od, cfg.value_hidden_layer_specs, 1, gen, self.dev)
+        self.opt_p = torch.optim.Adam(self.policy + [self.log_std], lr=cfg.lr_policy, eps=1e-8, capturable=True)
+        self.opt_v = torch.optim.Adam(self.value, lr=cfg.lr_value, eps=1e-8, capturable=True)
+        self.rms = RMS.create(od, self.dev)
+        self.gen = torch.Generator(device=self.dev).manual_seed(seed + 1000 * (self.rank + 1))
+        torch.cuda.manual_seed(seed + 7919 * (self.rank + 1))
+        keys = torch.from_numpy(parallel.rank_keys(seed, self.rank, self.n).view(np.int32)).to(self.dev)
+        (d, aux), obs = v_reset(keys)
+        self.state = (Data(d.qpos, d.qvel, d.qacc_warmstart, d.time), aux)
+        self.obs = obs
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        T, n = self.T, self.n
+        self.obs_traj, self.act_traj = torch.empty(T, n, od, **f32), torch.empty(T, n, nu, **f32)
+        self.logp_traj, self.r_traj = torch.empty(T, n, **f32), torch.empty(T, n, **f32)
+        self.term_traj, self.trunc_traj = torch.empty(T, n, **f32), torch.empty(T, n, **f32)
+        self.graph = None
+        self.use_graph = use_cuda_graph
+        self.n_grads = sum(p.numel() for p in self.policy + [self.log_std] + self.value)
+        self.timing: Dict[str, float] = {}
+
+    # ---------------------------------------------------------------- rollout (train_ppo.py:128-169)
+    def _rollout_body(self):
+        for t in range(self.T):
+            obs_n = self.rms.normalize(self.obs)
+            mean = _mlp_apply(self.policy, obs_n, self.nh_p)
+            eps = torch.randn(mean.shape, device=self.dev)              # default CUDA generator: graph-capture safe
+            act = mean + torch.exp(self.log_std) * eps
+            keys = torch.randint(-2 ** 31, 2 ** 31 - 1, (self.n, 2), device=self.dev, dtype=torch.int32)
+            self.obs_traj[t].copy_(self.obs)
+            self.act_traj[t].copy_(act)
+            self.logp_traj[t].copy_(gaussian_logprob(mean, self.log_std, act))
+            _, obs, r, te, tr = self.v_step.autoreset(self.state, act, keys, inplace=True)
+            self.r_traj[t].copy_(r)
+            self.term_traj[t].copy_(te)
+            self.trunc_traj[t].copy_(tr)
+            self.obs.copy_(obs)
+
+    @torch.no_grad()
+    def collect_rollout(self):
+        if not self.use_graph:
+            self._rollout_body()
+            return
+        if self.graph is None:
+            # warm-up outside capture (allocator pools, lazy library state, the overflow list), then capture the whole T-loop
+            s = torch.cuda.Stream(device=self.dev)
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                saved = [t.clone() for t in (self.state[0].qpos, self.state[0].qvel, self.state[0].qacc_warmstart, self.state[0].time,
+                                             self.state[1], self.obs)]
+                T_full, self.T = self.T, min(2, self.T)
+                self._rollout_body()
+                self.T = T_full
+                for dst, src in zip((self.state[0].qpos, self.state[0].qvel, self.state[0].qacc_warmstart, self.state[0].time,
+                                     self.state[1], self.obs), saved):
+                    dst.copy_(src)
+            torch.cuda.current_stream().wait_stream(s)
+            self.graph = torch.cuda.CUDAGraph()
+            self.rms_mean_buf, self.rms_var_buf = self.rms.mean.clone(), self.rms.var.clone()
+            graph_rms = RMS(self.rms_mean_buf, self.rms_var_buf, self.rms.count)
+            real_rms, self.rms = self.rms, graph_rms
+            with torch.cuda.graph(self.graph):
+                self._rollout_body()
+            self.rms = real_rms
+        self.rms_mean_buf.copy_(self.rms.mean)
+        self.rms_var_buf.copy_(self.rms.var)
+        self.graph.replay()
+
+    # ---------------------------------------------------------------- GAE (train_ppo.py:171-202)
+    @torch.no_grad()
+    def compute_gae(self, rewards, values, terminated, truncated):
+        g, lam = self.cfg.gamma, self.cfg.lam
+        delta = rewards + g * values[1:] * (1.0 - terminated) - values[:-1]          # [T, n] in three kernels
+        decay = g * lam * (1.0 - torch.maximum(terminated, truncated))
+        adv = torch.empty_like(rewards)
+        carry = torch.zeros_like(rewards[0])
+        for t in range(rewards.shape[0] - 1, -1, -1):                                 # reverse scan: one fused addcmul per step
+            carry = torch.addcmul(delta[t], decay[t], carry)
+            adv[t] = carry
+        return adv, adv + values[:-1]
+
+    def _allreduce_grads(self, params):
+        if self.world == 1:
+            return
+        flat = torch.cat([p.grad.reshape(-1) for p in params])
+        dist.all_reduce(flat)
+        flat /= self.world
+        o = 0
+        for p in params:
+            p.grad.copy_(flat[o:o + p.numel()].view_as(p.grad))
+            o += p.numel()
+
+    # ---------------------------------------------------------------- one PPO iteration (train_ppo.py:321-371)
+    def iteration(self) -> Dict[str, float]:
+        cfg, T, n = self.cfg, self.T, self.n
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
+        self.collect_rollout()
+        ev[1].record()
+        od = self.obs_traj.shape[-1]
+        with torch.no_grad():
+            self.rms.update(self.obs_traj.reshape(-1, od), self.world)
+            obs_norm = self.rms.normalize(self.obs_traj)
+            obs_last = self.rms.normalize(self.obs)
+            stack = torch.cat([obs_norm, obs_last.unsqueeze(0)], 0).reshape((T + 1) * n, od)
+            values = _mlp_apply(self.value, stack, self.nh_v).reshape(T + 1, n)
+            adv, ret = self.compute_gae(self.r_traj, values, self.term_traj, self.trunc_traj)
+        obs_f, act_f = obs_norm.reshape(T * n, od), self.act_traj.reshape(T * n, -1)
+        logp_f, adv_f, ret_f = self.logp_traj.reshape(-1), adv.reshape(-1), ret.reshape(-1)
+        total = T * n
+        mb = min(cfg.minibatch_size, total)
+        steps_per_epoch = total // mb
+        p_params = self.policy + [self.log_std]
+        for _ in range(cfg.epochs):
+            perm = torch.randperm(total, device=self.dev, generator=self.gen)[: steps_per_epoch * mb].view(steps_per_epoch, mb)
+            for idx in perm:
+                o, a, olp, r_, ad = obs_f[idx], act_f[idx], logp_f[idx], ret_f[idx], adv_f[idx]
+                mean = _mlp_apply(self.policy, o, self.nh_p)
+                logp = gaussian_logprob(mean, self.log_std, a)
+                ratio = torch.exp(logp - olp)
+                ad_n = (ad - ad.mean()) / (ad.std(unbiased=False) + 1e-8)
+                loss_p = -torch.minimum(ratio * ad_n, torch.clamp(ratio, 1 - cfg.clip_eps, 1 + cfg.clip_eps) * ad_n).mean()
+                entropy = 0.5 * torch.sum(1.0 + math.log(2.0 * math.pi) + 2.0 * self.log_std) / a.shape[-1]
+                loss = loss_p - cfg.ent_coef * entropy
+                self.opt_p.zero_grad(set_to_none=True)
+                self.opt_v.zero_grad(set_to_none=True)
+                loss.backward()
+                v = _mlp_apply(self.value, o, self.nh_v).squeeze(-1)
+                loss_v = torch.mean((v - r_) ** 2)
+                loss_v.backward()
+                self._allreduce_grads(p_params + self.value)
+                self.opt_p.step()
+                self.opt_v.step()
+        ev[2].record()
+        torch.cuda.synchronize()
+        done = torch.maximum(self.term_traj, self.trunc_traj).sum()
+        out = {"rollout_ms": ev[0].elapsed_time(ev[1]), "update_ms": ev[1].elapsed_time(ev[2]), "iter_ms": ev[0].elapsed_time(ev[2]),
+               "train_return_avg": float(self.r_traj.sum(0).mean()), "train_eplen_avg": float(total / max(float(done), 1.0)),
+               "minibatches": cfg.epochs * steps_per_epoch, "allreduce_floats": self.n_grads if self.world > 1 else 0}
+        return out
+
+
+def time_ppo(num_envs_local: int, rollout_length: int, iters: int = 5, warmup: int = 3, minibatch_size: int = 65536,
+             use_cuda_graph: bool = True, model=None, env_cfg=None) -> Dict[str, float]:
+    """Times PPO iterations (device-synchronised, max over ranks). Returns the mean over `iters` timed iterations."""
+    from . import modelc, training_utils
+    from .config import EnvConfig
+    cfg = PPOConfig()
+    cfg.rollout_length, cfg.minibatch_size, cfg.epochs = rollout_length, minibatch_size, 4         # reference src/config.json:117-120
+    cfg.lr_value, cfg.gamma = 3e-4, 0.99
+    cfg.env_config = env_cfg or EnvConfig(posture_penalty_weight=0.0, random_flip=True)
+    model = model or modelc.builtin_model("humanoid_mjx")
+    _, _, _, _, _, _, _, _, v_reset, v_step = training_utils.load_model_and_create_env("", cfg.env_config, model=model)
+    # JAX's default matmul precision on NVIDIA GPUs is TF32 for float32 operands (reference runs with jax defaults): same here
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    tr = PPOTrainer(cfg, v_reset, v_step, num_envs_local, use_cuda_graph=use_cuda_graph)
+    for _ in range(warmup):
+        tr.iteration()
+    parallel.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    acc = {"rollout_ms": 0.0, "update_ms": 0.0, "iter_ms": 0.0}
+    last = {}
+    for _ in range(iters):
+        last = tr.iteration()
+        for k in acc:
+            acc[k] += last[k]
+    torch.cuda.synchronize()
+    wall = parallel.max_over_ranks((time.perf_counter() - t0) / iters * 1e3, tr.dev)
+    res = {k: parallel.max_over_ranks(v / iters, tr.dev) for k, v in acc.items()}
+    res.update(wall_iter_ms=wall, envs_per_gpu=num_envs_local, rollout_length=rollout_length, world=tr.world,
+               env_steps_per_sec=num_envs_local * tr.world * rollout_length / (wall * 1e-3), minibatches=last.get("minibatches"),
+               allreduce_floats_per_minibatch=last.get("allreduce_floats"), train_return_avg=last.get("train_return_avg"),
+               cuda_graph=bool(use_cuda_graph))
+    return res
