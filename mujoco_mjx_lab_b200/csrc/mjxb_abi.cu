@@ -83,7 +83,6 @@ int build_dev_model(const mjxb_model_blob& b, const mjxb_env_config* cfg, DevMod
   if (b.nv != NV) return MJXB_EUNSUPPORTED;  // the in-register factorisation is compiled for nv = 27 (humanoid family)
   if (b.nbody > 32 || b.ngeom > 32 || b.nq > 32 || b.nlimit > 32 || b.ntlimit > 32 || b.nsensor > MJXB_MAXSENSOR) return MJXB_EUNSUPPORTED;
   if (b.solver != 2 && b.solver != 1) return MJXB_EUNSUPPORTED;
-  if (b.solver == 1) return MJXB_EUNSUPPORTED;  // CG variant: next stage (train_apg.py:101-105)
   D.nq = b.nq; D.nv = b.nv; D.nu = b.nu; D.nbody = b.nbody; D.njnt = b.njnt; D.ngeom = b.ngeom; D.nsite = b.nsite;
   D.ntendon = b.ntendon; D.nsensor = b.nsensor; D.npair = b.npair; D.ncon = b.ncon; D.nefc = b.nefc; D.nlimit = b.nlimit;
   D.ntlimit = b.ntlimit; D.ncon1 = b.ncon1; D.solver = b.solver; D.iterations = b.iterations; D.ls_iterations = b.ls_iterations;

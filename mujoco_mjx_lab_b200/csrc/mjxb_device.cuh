@@ -1033,7 +1033,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
       //   phase 1: Newton  Mgrad = (M + J^T D_act J)^-1 grad (mjx solver._update_gradient), repeated
       //   phase 2: qacc'   = (M + h*damping)^-1 (qfrc_smooth + qfrc_constraint)   (mjx forward.implicit / euler)
       float qas = 0.0f, qacc = 0.0f, Ma = 0.0f, qfc = 0.0f, grad = 0.0f, search = 0.0f;
-      float gauss = 0.0f, cost = 0.0f, prev_cost = 0.0f;
+      float gauss = 0.0f, cost = 0.0f, prev_cost = 0.0f, prev_grad = 0.0f, prev_Mgrad = 0.0f;
       int niter = 0, phase = 0;
       const float scale = 1.0f / (C.meaninertia * (float)max(1, C.nv));
       float qacc_int = 0.0f;
@@ -1088,7 +1088,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
 #pragma unroll
           for (int j = 0; j < NV; j++) a[j] += (j == lane) ? hd : 0.0f;
         }
-        if (phase == 1) {
+        if (phase == 1 && C.solver == 2) {  // Newton: H = M + J^T diag(D*active) J ; CG preconditions with M alone
           for (int r = 0; r < nrow; r++) {
             if (!(S.rJaref[r] < 0.0f)) continue;  // row inactive at the current iterate (warp-uniform)
             const float w = S.rD[r] * S.J[r * NVP + (lane < NVP ? lane : 0)];
@@ -1146,7 +1146,15 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
         if (phase == 2) { qacc_int = x; break; }
 
         // ---- phase 1: x = Mgrad
-        search = -x;
+        if (C.solver == 2 || niter == 0) {
+          search = -x;
+        } else {  // CG, Polak-Ribiere (mjx solver.solve body)
+          const float num = warp_sum((lane < NV) ? grad * (x - prev_Mgrad) : 0.0f);
+          const float den = warp_sum((lane < NV) ? prev_grad * prev_Mgrad : 0.0f);
+          const float beta = fmaxf(0.0f, num / fmaxf(MINVAL, den));
+          search = -x + beta * search;
+        }
+        prev_grad = grad; prev_Mgrad = x;
         // ---- line search along `search`: minimise f(alpha) = gauss-quadratic + sum_r [Jaref_r + alpha jv_r < 0] D_r (Jaref_r + alpha jv_r)^2 / 2
         {
           const float mv = matvec_M(S, lane, search);

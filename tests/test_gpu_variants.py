@@ -43,3 +43,11 @@ def test_lighten_solver_iterative_linesearch():
     model = helpers.load(overrides=dict(iterations=1, ls_iterations=1))
     dbg, ref = _compare(model, "lean", 500, tol_floor=1e-3)
     assert int(dbg["solver_niter"].max()) == 1 and int(ref["solver_niter"].max()) == 1
+
+
+def test_cg_solver_apg_settings():
+    """reference train_apg.py:101-105 solver_options: CG with iterations = ls_iterations = 4 (Polak-Ribiere, M-preconditioned)."""
+    from mujoco_mjx_lab_b200 import modelc
+    model = helpers.load(overrides=dict(solver=modelc.SOLVER_CG, iterations=4, ls_iterations=4))
+    dbg, ref = _compare(model, "lean", 600, tol_floor=1e-3)
+    assert int(ref["solver_niter"].max()) == 4 and int(dbg["solver_niter"].max()) == 4
