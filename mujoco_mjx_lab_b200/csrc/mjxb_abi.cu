@@ -32,6 +32,11 @@ struct Arena {  // device-resident env batch for the *_host entry points
   float *action = nullptr, *obs = nullptr, *reward = nullptr, *term = nullptr, *trunc = nullptr;
   uint32_t* keys = nullptr;
   cudaStream_t stream = nullptr;
+  // chunked host pipeline: H2D / kernel / D2H of consecutive env chunks overlap on separate streams, each with its own overflow list
+  static constexpr int kSlots = 3;
+  cudaStream_t pipe[kSlots] = {nullptr, nullptr, nullptr};
+  int* pipe_ovf[kSlots] = {nullptr, nullptr, nullptr};
+  int chunk = 0;
 };
 
 }  // namespace
@@ -56,6 +61,11 @@ void arena_free(Arena& a) {
   a.keys = nullptr;
   if (a.stream) cudaStreamDestroy(a.stream);
   a.stream = nullptr;
+  for (int i = 0; i < Arena::kSlots; i++) {
+    if (a.pipe[i]) cudaStreamDestroy(a.pipe[i]);
+    if (a.pipe_ovf[i]) cudaFree(a.pipe_ovf[i]);
+    a.pipe[i] = nullptr; a.pipe_ovf[i] = nullptr;
+  }
   a.n = 0;
 }
 
@@ -74,6 +84,19 @@ int arena_ensure(mjxb_model* m, int n) {
   CU(cudaMemsetAsync(a.qpos, 0, N * C.nq * 4, a.stream)); CU(cudaMemsetAsync(a.qvel, 0, N * C.nv * 4, a.stream));
   CU(cudaMemsetAsync(a.warm, 0, N * C.nv * 4, a.stream)); CU(cudaMemsetAsync(a.time, 0, N * 4, a.stream));
   CU(cudaMemsetAsync(a.aux, 0, N * MJXB_AUX_DIM * 4, a.stream));
+  // chunks of >= 65536 envs, at most 4 per step (each chunk still fills every SM for many rounds; every chunk pays its own
+  // overflow-consume launch, so more chunks stop paying off)
+  int nchunk = n / 65536;
+  if (nchunk < 1) nchunk = 1;
+  if (nchunk > 4) nchunk = 4;
+  { const char* e = getenv("MJXB_HOST_CHUNKS"); if (e && atoi(e) > 0) nchunk = atoi(e); }
+  a.chunk = (n + nchunk - 1) / nchunk;
+  for (int i = 0; i < Arena::kSlots; i++) {
+    CU(cudaStreamCreateWithFlags(&a.pipe[i], cudaStreamNonBlocking));
+    CU(cudaMalloc(&a.pipe_ovf[i], ((size_t)a.chunk + 2) * sizeof(int)));
+    CU(cudaMemsetAsync(a.pipe_ovf[i], 0, 2 * sizeof(int), a.stream));
+  }
+  CU(cudaStreamSynchronize(a.stream));
   a.n = n;
   return MJXB_OK;
 }
@@ -205,25 +228,26 @@ int build_dev_model(const mjxb_model_blob& b, const mjxb_env_config* cfg, DevMod
 
 using KMain = void (*)(const DevModel*, const PairParam*, StepArgs);
 
-int launch(const mjxb_model* mc, const StepArgs& args_in, bool dbg, cudaStream_t stream) {
+int launch(const mjxb_model* mc, const StepArgs& args_in, bool dbg, cudaStream_t stream, int* ovf_buf = nullptr) {
   mjxb_model* m = const_cast<mjxb_model*>(mc);  // the overflow list is library-owned scratch, grown on first use for a batch size
   int cur = 0;
   CU(cudaGetDevice(&cur));
   if (cur != m->device) CU(cudaSetDevice(m->device));
-  if (m->ovf_cap < args_in.n_env) {
+  if (ovf_buf == nullptr && m->ovf_cap < args_in.n_env) {
     if (m->ovf) { CU(cudaStreamSynchronize(stream)); CU(cudaFree(m->ovf)); m->ovf = nullptr; }
     CU(cudaMalloc(&m->ovf, ((size_t)args_in.n_env + 2) * sizeof(int)));
     CU(cudaMemsetAsync(m->ovf, 0, 2 * sizeof(int), stream));
     m->ovf_cap = args_in.n_env;
   }
   StepArgs args = args_in;
-  args.ovf_count = m->ovf; args.ovf_done = m->ovf + 1; args.ovf_list = m->ovf + 2; args.consume_overflow = 0;
+  int* ovf = ovf_buf ? ovf_buf : m->ovf;
+  args.ovf_count = ovf; args.ovf_done = ovf + 1; args.ovf_list = ovf + 2; args.consume_overflow = 0;
   { const char* e = getenv("MJXB_LOCKSTEP"); args.lockstep = e ? atoi(e) : 1; }  // default on; MJXB_LOCKSTEP=0 disables (profiling aid)
   { const char* e = getenv("MJXB_LOCKSTEP_GROUP"); args.lockstep_group = e ? atoi(e) : 0; }
   const int warps = m->warps;
   int grid = (args.n_env + warps - 1) / warps;
   if (grid > m->num_sms) grid = m->num_sms;
-  const bool ls = m->host.ls_exact != 0;
+  const bool ls = m->host.ls_exact != 0 && m->host.solver == 2;  // fast instantiation: Newton + exact line search; else the general one
 #define MJXB_LAUNCH(CAPv, CCv, Wv, G, B, SM)                                                                                   \
   do {                                                                                                                        \
     if (dbg && ls) mjxb_step_kernel<true, CAPv, CCv, Wv, true><<<G, B, SM, stream>>>(m->dev, m->dev_pp, args);                  \
@@ -433,22 +457,30 @@ static int step_host_impl(mjxb_model* m, int32_t n_env, const float* action_host
   if (!m || n_env <= 0 || !action_host || !obs_host || !reward_host || !terminated_host || !truncated_host) return MJXB_EINVAL;
   Arena& a = m->arena;
   if (a.n != n_env) return MJXB_EINVAL;  // reset_host / state_set_host must have created the batch
-  size_t N = (size_t)n_env;
-  CU(cudaMemcpyAsync(a.action, action_host, N * m->host.nu * 4, cudaMemcpyHostToDevice, a.stream));
-  int rc;
-  if (keys_host) {
-    CU(cudaMemcpyAsync(a.keys, keys_host, N * 8, cudaMemcpyHostToDevice, a.stream));
-    rc = mjxb_step_autoreset(m, n_env, arena_state(a), a.action, a.keys, arena_state(a), a.obs, a.reward, a.term, a.trunc, nullptr,
-                             nullptr, a.stream);
-  } else {
-    rc = mjxb_step(m, n_env, arena_state(a), a.action, arena_state(a), a.obs, a.reward, a.term, a.trunc, nullptr, a.stream);
+  const int nu = m->host.nu, od = m->host.cfg.obs_dim, nq = m->host.nq, nv = m->host.nv;
+  CU(cudaStreamSynchronize(a.stream));  // state_set_host / reset_host ran on a.stream
+  int slot = 0;
+  for (int lo = 0; lo < n_env; lo += a.chunk, slot = (slot + 1) % Arena::kSlots) {
+    const int cn = (n_env - lo < a.chunk) ? n_env - lo : a.chunk;
+    const size_t o = (size_t)lo, c = (size_t)cn;
+    cudaStream_t st = a.pipe[slot];
+    CU(cudaMemcpyAsync(a.action + o * nu, action_host + o * nu, c * nu * 4, cudaMemcpyHostToDevice, st));
+    if (keys_host) CU(cudaMemcpyAsync(a.keys + o * 2, keys_host + o * 2, c * 8, cudaMemcpyHostToDevice, st));
+    mjxb_state sv;
+    sv.qpos = a.qpos + o * nq; sv.qvel = a.qvel + o * nv; sv.qacc_warmstart = a.warm + o * nv; sv.time = a.time + o; sv.aux = a.aux + o * MJXB_AUX_DIM;
+    StepArgs sa;
+    memset(&sa, 0, sizeof(sa));
+    sa.n_env = cn; sa.mode = MODE_ENV_STEP; sa.nsteps = 1; sa.autoreset = keys_host ? 1 : 0; sa.in = sv; sa.out = sv;
+    sa.action = a.action + o * nu; sa.keys = keys_host ? a.keys + o * 2 : nullptr; sa.obs = a.obs + o * od; sa.reward = a.reward + o;
+    sa.terminated = a.term + o; sa.truncated = a.trunc + o;
+    int rc = launch(m, sa, false, st, a.pipe_ovf[slot]);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(obs_host + o * od, a.obs + o * od, c * od * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(reward_host + o, a.reward + o, c * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(terminated_host + o, a.term + o, c * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(truncated_host + o, a.trunc + o, c * 4, cudaMemcpyDeviceToHost, st));
   }
-  if (rc) return rc;
-  CU(cudaMemcpyAsync(obs_host, a.obs, N * m->host.cfg.obs_dim * 4, cudaMemcpyDeviceToHost, a.stream));
-  CU(cudaMemcpyAsync(reward_host, a.reward, N * 4, cudaMemcpyDeviceToHost, a.stream));
-  CU(cudaMemcpyAsync(terminated_host, a.term, N * 4, cudaMemcpyDeviceToHost, a.stream));
-  CU(cudaMemcpyAsync(truncated_host, a.trunc, N * 4, cudaMemcpyDeviceToHost, a.stream));
-  CU(cudaStreamSynchronize(a.stream));
+  for (int i = 0; i < Arena::kSlots; i++) CU(cudaStreamSynchronize(a.pipe[i]));
   return MJXB_OK;
 }
 

@@ -1088,7 +1088,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
 #pragma unroll
           for (int j = 0; j < NV; j++) a[j] += (j == lane) ? hd : 0.0f;
         }
-        if (phase == 1 && C.solver == 2) {  // Newton: H = M + J^T diag(D*active) J ; CG preconditions with M alone
+        if (phase == 1 && (LS_EXACT || C.solver == 2)) {  // Newton: H = M + J^T diag(D*active) J ; CG preconditions with M alone
           for (int r = 0; r < nrow; r++) {
             if (!(S.rJaref[r] < 0.0f)) continue;  // row inactive at the current iterate (warp-uniform)
             const float w = S.rD[r] * S.J[r * NVP + (lane < NVP ? lane : 0)];
@@ -1146,7 +1146,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
         if (phase == 2) { qacc_int = x; break; }
 
         // ---- phase 1: x = Mgrad
-        if (C.solver == 2 || niter == 0) {
+        if (LS_EXACT || C.solver == 2 || niter == 0) {  // (the LS_EXACT instantiation is Newton-only)
           search = -x;
         } else {  // CG, Polak-Ribiere (mjx solver.solve body)
           const float num = warp_sum((lane < NV) ? grad * (x - prev_Mgrad) : 0.0f);
@@ -1154,7 +1154,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
           const float beta = fmaxf(0.0f, num / fmaxf(MINVAL, den));
           search = -x + beta * search;
         }
-        prev_grad = grad; prev_Mgrad = x;
+        if (!LS_EXACT) { prev_grad = grad; prev_Mgrad = x; }
         // ---- line search along `search`: minimise f(alpha) = gauss-quadratic + sum_r [Jaref_r + alpha jv_r < 0] D_r (Jaref_r + alpha jv_r)^2 / 2
         {
           const float mv = matvec_M(S, lane, search);
