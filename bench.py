@@ -234,6 +234,13 @@ def main():
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    traffic = None                                                # dram bytes per step launch from the committed ncu capture
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        if int(tj["n_env"]) == n:
+            traffic = float(tj["dram_bytes_per_launch"])
+    except Exception:
+        pass
     kernel_ms = ms_step                                           # one step == one step-kernel launch (+ an empty overflow pass)
     ach_gbs = ALG_BYTES_PER_STEP * n / (kernel_ms * 1e-3) / 1e9
     ach_tflops = flops * n / (kernel_ms * 1e-3) / 1e12
@@ -246,7 +253,7 @@ def main():
         "gpu_launches": 2 * args.steps,
         "kernels": ["mjxb_step_kernel<false,32,16,16> (step)", "mjxb_step_kernel<false,320,176,3> (overflow re-run; exits at once when empty)"],
         "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                     "traffic": None, "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 (of fallback)",
+                     "traffic": traffic, "algorithmic_bytes_per_launch": ALG_BYTES_PER_STEP * n, "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 (of fallback)",
                      "algorithmic_bytes_per_env_step": ALG_BYTES_PER_STEP, "kernel_ms": kernel_ms,
                      "note": "the step is FP32-pipe/latency bound, ~16x under its HBM ceiling; see roofline_fp32"},
         "roofline_fp32": {"bound": "fp32 CUDA cores", "achieved": ach_tflops, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
