@@ -244,9 +244,13 @@ int launch(const mjxb_model* mc, const StepArgs& args_in, bool dbg, cudaStream_t
   args.ovf_count = ovf; args.ovf_done = ovf + 1; args.ovf_list = ovf + 2; args.consume_overflow = 0;
   { const char* e = getenv("MJXB_LOCKSTEP"); args.lockstep = e ? atoi(e) : 1; }  // default on; MJXB_LOCKSTEP=0 disables (profiling aid)
   { const char* e = getenv("MJXB_LOCKSTEP_GROUP"); args.lockstep_group = e ? atoi(e) : 0; }
-  const int warps = m->warps;
+  // small batches: spread the envs over every SM (fewer warps per CTA run faster than 16 sharing one SM's issue slots)
+  int warps = m->warps;
+  const int per_sm = (args.n_env + m->num_sms - 1) / m->num_sms;
+  if (per_sm < warps) warps = per_sm < 1 ? 1 : per_sm;
   int grid = (args.n_env + warps - 1) / warps;
   if (grid > m->num_sms) grid = m->num_sms;
+  const size_t smem_main = m->smem - (size_t)(m->warps - warps) * sizeof(WarpS<CAP_MAIN, MAXCC_MAIN>);
   const bool ls = m->host.ls_exact != 0 && m->host.solver == 2;  // fast instantiation: Newton + exact line search; else the general one
 #define MJXB_LAUNCH(CAPv, CCv, Wv, G, B, SM)                                                                                   \
   do {                                                                                                                        \
@@ -255,7 +259,7 @@ int launch(const mjxb_model* mc, const StepArgs& args_in, bool dbg, cudaStream_t
     else if (ls) mjxb_step_kernel<false, CAPv, CCv, Wv, true><<<G, B, SM, stream>>>(m->dev, m->dev_pp, args);                   \
     else mjxb_step_kernel<false, CAPv, CCv, Wv, false><<<G, B, SM, stream>>>(m->dev, m->dev_pp, args);                          \
   } while (0)
-  MJXB_LAUNCH(CAP_MAIN, MAXCC_MAIN, WARPS_MAIN, grid, warps * 32, m->smem);
+  MJXB_LAUNCH(CAP_MAIN, MAXCC_MAIN, WARPS_MAIN, grid, warps * 32, smem_main);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) {  // big-capacity pass over the envs the main pass could not hold (usually none: exits at once)
     args.consume_overflow = 1;
