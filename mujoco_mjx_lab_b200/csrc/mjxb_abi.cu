@@ -45,9 +45,9 @@ struct mjxb_model {
   DevModel host;
   DevModel* dev = nullptr;
   PairParam* dev_pp = nullptr;
-  int device = 0, num_sms = 0, warps = 0, warps_big = 0;
-  size_t smem = 0, smem_big = 0;
-  int* ovf = nullptr;   // [0] count, [1] done, [2..] env list
+  int device = 0, num_sms = 0, warps = 0, warps_mid = 0, warps_big = 0;
+  size_t smem = 0, smem_mid = 0, smem_big = 0;
+  int* ovf = nullptr;   // [0] countA, [1] doneA, [2] countB, [3] doneB, [4..4+cap) listA (main -> mid), [4+cap..) listB (mid -> big)
   int ovf_cap = 0;
   Arena arena;
 };
@@ -93,8 +93,8 @@ int arena_ensure(mjxb_model* m, int n) {
   a.chunk = (n + nchunk - 1) / nchunk;
   for (int i = 0; i < Arena::kSlots; i++) {
     CU(cudaStreamCreateWithFlags(&a.pipe[i], cudaStreamNonBlocking));
-    CU(cudaMalloc(&a.pipe_ovf[i], ((size_t)a.chunk + 2) * sizeof(int)));
-    CU(cudaMemsetAsync(a.pipe_ovf[i], 0, 2 * sizeof(int), a.stream));
+    CU(cudaMalloc(&a.pipe_ovf[i], (2 * (size_t)a.chunk + 4) * sizeof(int)));
+    CU(cudaMemsetAsync(a.pipe_ovf[i], 0, 4 * sizeof(int), a.stream));
   }
   CU(cudaStreamSynchronize(a.stream));
   a.n = n;
@@ -228,20 +228,23 @@ int build_dev_model(const mjxb_model_blob& b, const mjxb_env_config* cfg, DevMod
 
 using KMain = void (*)(const DevModel*, const PairParam*, StepArgs);
 
-int launch(const mjxb_model* mc, const StepArgs& args_in, bool dbg, cudaStream_t stream, int* ovf_buf = nullptr) {
+int launch(const mjxb_model* mc, const StepArgs& args_in, bool dbg, cudaStream_t stream, int* ovf_buf = nullptr, int ovf_buf_cap = 0) {
   mjxb_model* m = const_cast<mjxb_model*>(mc);  // the overflow list is library-owned scratch, grown on first use for a batch size
   int cur = 0;
   CU(cudaGetDevice(&cur));
   if (cur != m->device) CU(cudaSetDevice(m->device));
   if (ovf_buf == nullptr && m->ovf_cap < args_in.n_env) {
     if (m->ovf) { CU(cudaStreamSynchronize(stream)); CU(cudaFree(m->ovf)); m->ovf = nullptr; }
-    CU(cudaMalloc(&m->ovf, ((size_t)args_in.n_env + 2) * sizeof(int)));
-    CU(cudaMemsetAsync(m->ovf, 0, 2 * sizeof(int), stream));
+    CU(cudaMalloc(&m->ovf, (2 * (size_t)args_in.n_env + 4) * sizeof(int)));
+    CU(cudaMemsetAsync(m->ovf, 0, 4 * sizeof(int), stream));
     m->ovf_cap = args_in.n_env;
   }
   StepArgs args = args_in;
   int* ovf = ovf_buf ? ovf_buf : m->ovf;
-  args.ovf_count = ovf; args.ovf_done = ovf + 1; args.ovf_list = ovf + 2; args.consume_overflow = 0;
+  const int cap = ovf_buf ? ovf_buf_cap : m->ovf_cap;
+  int* listA = ovf + 4;
+  int* listB = ovf + 4 + cap;
+  args.in_count = nullptr; args.in_list = nullptr; args.in_done = nullptr; args.out_count = ovf; args.out_list = listA;
   { const char* e = getenv("MJXB_LOCKSTEP"); args.lockstep = e ? atoi(e) : 1; }  // default on; MJXB_LOCKSTEP=0 disables (profiling aid)
   { const char* e = getenv("MJXB_LOCKSTEP_GROUP"); args.lockstep_group = e ? atoi(e) : 0; }
   // small batches: spread the envs over every SM (fewer warps per CTA run faster than 16 sharing one SM's issue slots)
@@ -261,8 +264,16 @@ int launch(const mjxb_model* mc, const StepArgs& args_in, bool dbg, cudaStream_t
   } while (0)
   MJXB_LAUNCH(CAP_MAIN, MAXCC_MAIN, WARPS_MAIN, grid, warps * 32, smem_main);
   cudaError_t e = cudaGetLastError();
-  if (e == cudaSuccess) {  // big-capacity pass over the envs the main pass could not hold (usually none: exits at once)
-    args.consume_overflow = 1;
+  if (e == cudaSuccess) {  // mid tier (64 rows / 24 contacts) over the envs the main tile could not hold; usually few: exits at once when empty
+    args.in_count = ovf; args.in_done = ovf + 1; args.in_list = listA; args.out_count = ovf + 2; args.out_list = listB;
+    const int wm = m->warps_mid;
+    int gridm = m->num_sms;
+    if (gridm * wm > args.n_env) gridm = (args.n_env + wm - 1) / wm;
+    MJXB_LAUNCH(CAP_MID, MAXCC_MID, WARPS_MID, gridm, wm * 32, m->smem_mid);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) {  // big tier: holds every static row / contact slot of the model
+    args.in_count = ovf + 2; args.in_done = ovf + 3; args.in_list = listB; args.out_count = nullptr; args.out_list = nullptr;
     const int wb = m->warps_big;
     int gridb = m->num_sms;
     if (gridb * wb > args.n_env) gridb = (args.n_env + wb - 1) / wb;
@@ -328,16 +339,21 @@ int mjxb_model_create(const void* blob, size_t blob_bytes, const mjxb_env_config
   const size_t model_bytes = (sizeof(DevModel) + 15) & ~size_t(15);
   const size_t avail = prop.sharedMemPerBlockOptin;
   using WSMain = WarpS<CAP_MAIN, MAXCC_MAIN>;
+  using WSMid = WarpS<CAP_MID, MAXCC_MID>;
   using WSBig = WarpS<CAP_BIG, MAXCC_BIG>;
-  int warps = (int)((avail - model_bytes) / sizeof(WSMain)), warps_big = (int)((avail - model_bytes) / sizeof(WSBig));
+  int warps = (int)((avail - model_bytes) / sizeof(WSMain)), warps_mid = (int)((avail - model_bytes) / sizeof(WSMid)),
+      warps_big = (int)((avail - model_bytes) / sizeof(WSBig));
   if (warps > WARPS_MAIN) warps = WARPS_MAIN;
+  if (warps_mid > WARPS_MID) warps_mid = WARPS_MID;
   if (warps_big > WARPS_BIG) warps_big = WARPS_BIG;
-  if (warps < 1 || warps_big < 1) { delete m; cudaSetDevice(cur); return MJXB_EUNSUPPORTED; }
-  m->warps = warps; m->warps_big = warps_big;
+  if (warps < 1 || warps_mid < 1 || warps_big < 1) { delete m; cudaSetDevice(cur); return MJXB_EUNSUPPORTED; }
+  m->warps = warps; m->warps_mid = warps_mid; m->warps_big = warps_big;
   m->smem = model_bytes + (size_t)warps * sizeof(WSMain);
+  m->smem_mid = model_bytes + (size_t)warps_mid * sizeof(WSMid);
   m->smem_big = model_bytes + (size_t)warps_big * sizeof(WSBig);
 #define MJXB_SMEM_ATTR(DBGv, LSv)                                                                                                         \
   CUX(cudaFuncSetAttribute(mjxb_step_kernel<DBGv, CAP_MAIN, MAXCC_MAIN, WARPS_MAIN, LSv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem)); \
+  CUX(cudaFuncSetAttribute(mjxb_step_kernel<DBGv, CAP_MID, MAXCC_MID, WARPS_MID, LSv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_mid)); \
   CUX(cudaFuncSetAttribute(mjxb_step_kernel<DBGv, CAP_BIG, MAXCC_BIG, WARPS_BIG, LSv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_big));
   MJXB_SMEM_ATTR(false, true) MJXB_SMEM_ATTR(true, true) MJXB_SMEM_ATTR(false, false) MJXB_SMEM_ATTR(true, false)
 #undef MJXB_SMEM_ATTR
@@ -368,7 +384,7 @@ int mjxb_model_dims(const mjxb_model* m, int32_t dims[8]) {
   return MJXB_OK;
 }
 
-size_t mjxb_model_scratch_bytes(const mjxb_model* m) { return m ? ((size_t)m->ovf_cap + 2) * sizeof(int) : 0; }
+size_t mjxb_model_scratch_bytes(const mjxb_model* m) { return m ? (2 * (size_t)m->ovf_cap + 4) * sizeof(int) : 0; }
 
 int mjxb_launch_config(const mjxb_model* m, int32_t cfg[4]) {  // warps per CTA, dynamic smem bytes, SM count, sizeof(WarpS)
   if (!m || !cfg) return MJXB_EINVAL;
@@ -477,7 +493,7 @@ static int step_host_impl(mjxb_model* m, int32_t n_env, const float* action_host
     sa.n_env = cn; sa.mode = MODE_ENV_STEP; sa.nsteps = 1; sa.autoreset = keys_host ? 1 : 0; sa.in = sv; sa.out = sv;
     sa.action = a.action + o * nu; sa.keys = keys_host ? a.keys + o * 2 : nullptr; sa.obs = a.obs + o * od; sa.reward = a.reward + o;
     sa.terminated = a.term + o; sa.truncated = a.trunc + o;
-    int rc = launch(m, sa, false, st, a.pipe_ovf[slot]);
+    int rc = launch(m, sa, false, st, a.pipe_ovf[slot], a.chunk);
     if (rc) return rc;
     CU(cudaMemcpyAsync(obs_host + o * od, a.obs + o * od, c * od * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(reward_host + o, a.reward + o, c * 4, cudaMemcpyDeviceToHost, st));

@@ -28,6 +28,7 @@ constexpr int NVP = 28;   // row stride (floats) of M and J: 16-byte aligned row
 #define MJXB_WARPS_MAIN 16
 #endif
 constexpr int CAP_MAIN = MJXB_CAP_MAIN, MAXCC_MAIN = MJXB_MAXCC_MAIN, WARPS_MAIN = MJXB_WARPS_MAIN;
+constexpr int CAP_MID = 64, MAXCC_MID = 24, WARPS_MID = 10;
 constexpr int CAP_BIG = 320, MAXCC_BIG = 176, WARPS_BIG = 3;
 constexpr unsigned FULL = 0xffffffffu;
 constexpr float MINVAL = 1e-15f;
@@ -81,10 +82,10 @@ struct StepArgs {
   int32_t* status;
   const float* vel;      // speed test
   float* pos;
-  int* ovf_count;        // overflow protocol (library-owned): main pass appends, big pass consumes and resets
-  int* ovf_list;
-  int* ovf_done;
-  int consume_overflow;  // 1: this launch iterates over ovf_list instead of 0..n_env
+  // overflow protocol (library-owned scratch): a pass iterates over `in_list` (NULL: all envs 0..n_env), appends the envs its
+  // row tile cannot hold to `out_list` (NULL: none -- the last tier holds every static row), and resets its input list when done
+  int* in_count; int* in_list; int* in_done;
+  int* out_count; int* out_list;
   int lockstep;          // CTA barriers keep the warps of an SM in the same code region (instruction-cache locality)
   int lockstep_group;    // warps per barrier group (0 = the whole CTA)
   mjxb_debug dbg;
@@ -434,7 +435,8 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
   const mjxb_env_config& cfg = C.cfg;
   const int nbody = C.nbody;
 
-  const int n_items = A.consume_overflow ? *reinterpret_cast<volatile int*>(A.ovf_count) : A.n_env;
+  const bool consuming = A.in_list != nullptr;
+  const int n_items = consuming ? *reinterpret_cast<volatile int*>(A.in_count) : A.n_env;
   const int n_rounds = (n_items + gridDim.x * nwarp - 1) / (gridDim.x * nwarp);
   for (int round = 0; round < n_rounds; round++) {
     if (A.lockstep > 0) group_sync(warp, A.lockstep_group);
@@ -442,12 +444,12 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
     // Warps without work in the last round (and envs that overflow the row tile) still run the whole pipeline -- on env 0 /
     // on a truncated row set -- with every global store suppressed, so that all warps of the CTA reach the same barriers.
     const bool valid = item < n_items;
-    const int env = valid ? (A.consume_overflow ? A.ovf_list[item] : item) : (A.consume_overflow ? A.ovf_list[0] : 0);
+    const int env = valid ? (consuming ? A.in_list[item] : item) : (consuming ? A.in_list[0] : 0);
     bool overflow = false;
     // ---------------------------------------------------------------- load state (lane d <-> qpos[d], qvel[d], ...)
     int mode = A.mode;
     float q = 0.0f, v = 0.0f, ws = 0.0f, ctrl = 0.0f, tm = 0.0f, aux = 0.0f, action = 0.0f;
-    int status = A.consume_overflow ? MJXB_STATUS_ROW_SPILL : 0;
+    int status = consuming ? MJXB_STATUS_ROW_SPILL : 0;
     if (mode == MODE_ENV_STEP || mode == MODE_PHYS_STEP || mode == MODE_FORWARD) {
       if (lane < C.nq) q = A.in.qpos[(size_t)env * C.nq + lane];
       if (lane < NV) { v = A.in.qvel[(size_t)env * NV + lane]; ws = A.in.qacc_warmstart[(size_t)env * NV + lane]; }
@@ -1483,8 +1485,8 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
     }  // nsteps
     if (!valid) continue;
     if (overflow) {  // leave the env untouched; the big-capacity pass redoes it from its inputs
-      if (A.ovf_list != nullptr && !A.consume_overflow) {
-        if (lane == 0) { const int slot = atomicAdd(A.ovf_count, 1); A.ovf_list[slot] = env; }
+      if (A.out_list != nullptr) {
+        if (lane == 0) { const int slot = atomicAdd(A.out_count, 1); A.out_list[slot] = env; }
       } else if (A.status && lane == 0) {
         A.status[env] = status | MJXB_STATUS_ROW_SPILL;
       }
@@ -1510,12 +1512,12 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
     if (A.status && lane == 0) A.status[env] = status;
     __syncwarp();
   }
-  if (A.consume_overflow) {  // last CTA out resets the overflow counters for the next main launch
+  if (consuming) {  // last CTA out resets the consumed list's counters for the next step
     __syncthreads();
     if (threadIdx.x == 0) {
       __threadfence();
-      const int t = atomicAdd(A.ovf_done, 1);
-      if (t == (int)gridDim.x - 1) { *A.ovf_count = 0; *A.ovf_done = 0; __threadfence(); }
+      const int t = atomicAdd(A.in_done, 1);
+      if (t == (int)gridDim.x - 1) { *A.in_count = 0; *A.in_done = 0; __threadfence(); }
     }
   }
 }

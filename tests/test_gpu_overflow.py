@@ -1,4 +1,4 @@
-"""Envs whose candidate rows exceed the shared-memory tile are re-run by the big-capacity instantiation: same results."""
+"""Envs whose candidate rows exceed the 32-row shared-memory tile are re-run by the mid (64 rows) and big (320 rows) tiers: same results."""
 import numpy as np
 import pytest
 import torch
@@ -18,6 +18,7 @@ def test_overflow_envs_match_oracle(model, oracle):
     ncand = (ref["efc_active"] & 1).sum(axis=1)
     big = ncand > 32
     assert big.sum() >= 3, "seed no longer produces overflowing envs"
+    assert ((ncand > 32) & (ncand <= 60)).sum() >= 3 and (ncand > 66).sum() >= 1, "need envs for both the mid and the big tier"
     t = lambda a: torch.tensor(a, dtype=torch.float32, device="cuda")
     _, out = mjx.forward(sysm, mjx.Data(t(q), t(v), t(w), torch.zeros(n, device="cuda"), t(c)), debug=True)
     status = out["status"].cpu().numpy()
