@@ -169,6 +169,64 @@ int build_dev_model(const mjxb_model_blob& b, const mjxb_env_config* cfg, DevMod
       D.qpos_kind[qa] = QK_HINGE; D.qpos_aux[qa] = da;
     }
   }
+  // joint tree + body/dof tables for the prefix-composition kinematics
+  {
+    int body_lastjnt[MJXB_MAXBODY];
+    for (int i = 0; i < b.nbody; i++) body_lastjnt[i] = b.body_jntnum[i] > 0 ? b.body_jntadr[i] + b.body_jntnum[i] - 1 : -1;
+    int maxchain = 1;
+    for (int j = 0; j < b.njnt; j++) {
+      const int bd = b.jnt_body[j];
+      D.jnt_bodyid[j] = bd;
+      D.jnt_first[j] = (j == b.body_jntadr[bd]) ? 1 : 0;
+      int par = -1;
+      if (!D.jnt_first[j]) par = j - 1;
+      else {
+        int a = b.body_parent[bd];
+        // fixed offsets of joint-less bodies between bd and its nearest jointed ancestor are not supported for a FIRST joint
+        if (a > 0 && body_lastjnt[a] < 0) return MJXB_EUNSUPPORTED;
+        par = a > 0 ? body_lastjnt[a] : -1;
+      }
+      if (b.jnt_type[j] == 0 && (par >= 0 || b.body_parent[bd] != 0)) return MJXB_EUNSUPPORTED;  // free joints only on top-level bodies
+      D.jnt_parent[j] = par;
+    }
+    for (int j = 0; j < b.njnt; j++) { int n = 1; for (int a = D.jnt_parent[j]; a >= 0; a = D.jnt_parent[a]) n++; if (n > maxchain) maxchain = n; }
+    for (int d = 0; d < b.nv; d++) { int n = 1; for (int a = b.dof_parent[d]; a >= 0; a = b.dof_parent[a]) n++; if (n > maxchain) maxchain = n; }
+    D.tree_steps = 0;
+    while ((1 << D.tree_steps) < maxchain) D.tree_steps++;
+    for (int i = 0; i < b.nbody; i++) {
+      // body frame = frame after joint srcjnt composed with (relpos, relquat); joint-less bodies accumulate their fixed offsets
+      double rp[3] = {0, 0, 0}, rq[4] = {1, 0, 0, 0};
+      int a = i;
+      while (a > 0 && body_lastjnt[a] < 0) {  // prepend body a's offset: T_a o (rp, rq)
+        const double w = b.body_quat[a][0], x = b.body_quat[a][1], y = b.body_quat[a][2], z = b.body_quat[a][3];
+        const double R[9] = {w * w + x * x - y * y - z * z, 2 * (x * y - w * z), 2 * (x * z + w * y), 2 * (x * y + w * z), w * w - x * x + y * y - z * z,
+                             2 * (y * z - w * x), 2 * (x * z - w * y), 2 * (y * z + w * x), w * w - x * x - y * y + z * z};
+        const double np[3] = {b.body_pos[a][0] + R[0] * rp[0] + R[1] * rp[1] + R[2] * rp[2], b.body_pos[a][1] + R[3] * rp[0] + R[4] * rp[1] + R[5] * rp[2],
+                              b.body_pos[a][2] + R[6] * rp[0] + R[7] * rp[1] + R[8] * rp[2]};
+        const double nq[4] = {w * rq[0] - x * rq[1] - y * rq[2] - z * rq[3], w * rq[1] + x * rq[0] + y * rq[3] - z * rq[2],
+                              w * rq[2] - x * rq[3] + y * rq[0] + z * rq[1], w * rq[3] + x * rq[2] - y * rq[1] + z * rq[0]};
+        for (int k = 0; k < 3; k++) rp[k] = np[k];
+        for (int k = 0; k < 4; k++) rq[k] = nq[k];
+        a = b.body_parent[a];
+      }
+      D.body_srcjnt[i] = a > 0 ? body_lastjnt[a] : -1;
+      for (int k = 0; k < 3; k++) D.body_relpos[i][k] = (float)rp[k];
+      for (int k = 0; k < 4; k++) D.body_relquat[i][k] = (float)rq[k];
+      int bb = i;
+      while (bb > 0 && b.body_dofnum[bb] == 0) bb = b.body_parent[bb];
+      D.body_lastdof[i] = bb > 0 ? b.body_dofadr[bb] + b.body_dofnum[bb] - 1 : -1;
+    }
+    for (int d = 0; d < MJXB_MAXDOF; d++) D.dof_cvel_src[d] = -2;
+    for (int d = 0; d < b.nv; d++) {
+      const int j = b.dof_jnt[d];
+      if (b.jnt_type[j] == 0) {
+        const int k = d - b.jnt_dofadr[j];
+        D.dof_cvel_src[d] = k < 3 ? -2 : b.jnt_dofadr[j] + 2;   // linear: cdof_dot = 0; angular: velocity after the three linear dofs
+      } else {
+        D.dof_cvel_src[d] = b.dof_parent[d];                    // -1: nothing moves before this dof
+      }
+    }
+  }
   // dofs that move each body: walk the dof-parent chain from the body's (or nearest jointed ancestor's) last dof
   for (int i = 1; i < b.nbody; i++) {
     int bb = i;

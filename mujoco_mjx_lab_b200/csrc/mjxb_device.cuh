@@ -51,6 +51,11 @@ struct DevModel {
   float body_pos[MJXB_MAXBODY][3], body_quat[MJXB_MAXBODY][4], body_ipos[MJXB_MAXBODY][3], body_inertia[MJXB_MAXBODY][6],
       body_mass[MJXB_MAXBODY];
   int jnt_type[MJXB_MAXJNT], jnt_qposadr[MJXB_MAXJNT], jnt_dofadr[MJXB_MAXJNT];
+  int jnt_parent[MJXB_MAXJNT], jnt_first[MJXB_MAXJNT], jnt_bodyid[MJXB_MAXJNT];  // joint tree (previous joint up the chain), first joint of its body
+  int body_srcjnt[MJXB_MAXBODY], body_lastdof[MJXB_MAXBODY];  // joint whose frame carries the body; last dof moving the body (-1: none)
+  float body_relpos[MJXB_MAXBODY][3], body_relquat[MJXB_MAXBODY][4];  // fixed offset of the body frame from that joint frame
+  int dof_cvel_src[MJXB_MAXDOF];  // dof whose inclusive velocity prefix is 'cvel before this dof' (-1: zero, -2: cdof_dot = 0)
+  int tree_steps;  // pointer-jumping rounds covering the deepest joint / dof chain
   float jnt_pos[MJXB_MAXJNT][3], jnt_axis[MJXB_MAXJNT][3];
   int lim_dof[MJXB_MAXJNT], lim_qadr[MJXB_MAXJNT], lim_row[MJXB_MAXJNT];
   float lim_range[MJXB_MAXJNT][2], lim_invweight[MJXB_MAXJNT], lim_solref[MJXB_MAXJNT][2], lim_solimp[MJXB_MAXJNT][5];
@@ -515,47 +520,81 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
       S.vec[VCTRL][lane] = ctrl;
       __syncwarp();
 
-      // ---------------------------------------------------------------- kinematics (level-synchronous over the body tree)
-      if (lane == 0) {
-        S.a.xpos[0][0] = S.a.xpos[0][1] = S.a.xpos[0][2] = 0.0f;
-        S.a.xquat[0][0] = 1.0f; S.a.xquat[0][1] = S.a.xquat[0][2] = S.a.xquat[0][3] = 0.0f;
-      }
-      __syncwarp();
-      for (int lev = 1; lev <= C.maxdepth; lev++) {
-        if (lane < nbody && C.body_depth[lane] == lev) {
-          const int b = lane, p = C.body_parent[b];
-          float pq[4] = {S.a.xquat[p][0], S.a.xquat[p][1], S.a.xquat[p][2], S.a.xquat[p][3]};
-          float pos[3], quat[4], t[3];
-          rotq(t, C.body_pos[b], pq);
-          pos[0] = S.a.xpos[p][0] + t[0]; pos[1] = S.a.xpos[p][1] + t[1]; pos[2] = S.a.xpos[p][2] + t[2];
-          quat_mul(quat, pq, C.body_quat[b]);
-          for (int j = C.body_jntadr[b]; j < C.body_jntadr[b] + C.body_jntnum[b]; j++) {
-            const int qa = C.jnt_qposadr[j], da = C.jnt_dofadr[j];
-            if (C.jnt_type[j] == 0) {
-              pos[0] = S.vec[VQPOS][qa]; pos[1] = S.vec[VQPOS][qa + 1]; pos[2] = S.vec[VQPOS][qa + 2];
-              float w = S.vec[VQPOS][qa + 3], x = S.vec[VQPOS][qa + 4], y = S.vec[VQPOS][qa + 5], z = S.vec[VQPOS][qa + 6];
-              float n = sqrtf(w * w + x * x + y * y + z * z);
-              float dn = n + (n == 0.0f ? 1e-6f : 0.0f);
-              quat[0] = w / dn; quat[1] = x / dn; quat[2] = y / dn; quat[3] = z / dn;
-              S.vec[VQPOS][qa + 3] = quat[0]; S.vec[VQPOS][qa + 4] = quat[1]; S.vec[VQPOS][qa + 5] = quat[2]; S.vec[VQPOS][qa + 6] = quat[3];
+      // ---------------------------------------------------------------- kinematics: parallel prefix over the joint tree
+      // Lane j holds the rigid transform of joint j relative to the frame before it (body offset folded into a body's first joint);
+      // log2(depth) rounds of pointer jumping with shuffles compose it up the chain to the world frame after the joint. The joint
+      // anchor and axis are invariant under the joint's own rotation, so they are read off that frame (mjx smooth.kinematics).
+      {
+        float ep[3] = {0.0f, 0.0f, 0.0f}, eq[4] = {1.0f, 0.0f, 0.0f, 0.0f};
+        int jp = -1;
+        if (lane < C.njnt) {
+          const int j = lane, qa = C.jnt_qposadr[j];
+          jp = C.jnt_parent[j];
+          if (C.jnt_type[j] == 0) {
+            ep[0] = S.vec[VQPOS][qa]; ep[1] = S.vec[VQPOS][qa + 1]; ep[2] = S.vec[VQPOS][qa + 2];
+            float w = S.vec[VQPOS][qa + 3], x = S.vec[VQPOS][qa + 4], y = S.vec[VQPOS][qa + 5], z = S.vec[VQPOS][qa + 6];
+            float n = sqrtf(w * w + x * x + y * y + z * z);
+            float dn = 1.0f / (n + (n == 0.0f ? 1e-6f : 0.0f));
+            eq[0] = w * dn; eq[1] = x * dn; eq[2] = y * dn; eq[3] = z * dn;
+            S.vec[VQPOS][qa + 3] = eq[0]; S.vec[VQPOS][qa + 4] = eq[1]; S.vec[VQPOS][qa + 5] = eq[2]; S.vec[VQPOS][qa + 6] = eq[3];
+          } else {
+            float ang = S.vec[VQPOS][qa] - C.qpos0[qa], sn, cs, t[3];
+            sincosf(ang * 0.5f, &sn, &cs);
+            float ql[4] = {cs, C.jnt_axis[j][0] * sn, C.jnt_axis[j][1] * sn, C.jnt_axis[j][2] * sn};
+            rotq(t, C.jnt_pos[j], ql);
+            float dp[3] = {C.jnt_pos[j][0] - t[0], C.jnt_pos[j][1] - t[1], C.jnt_pos[j][2] - t[2]};  // rotation about the anchor
+            if (C.jnt_first[j]) {
+              const int b = C.jnt_bodyid[j];
+              rotq(t, dp, C.body_quat[b]);
+              ep[0] = C.body_pos[b][0] + t[0]; ep[1] = C.body_pos[b][1] + t[1]; ep[2] = C.body_pos[b][2] + t[2];
+              quat_mul(eq, C.body_quat[b], ql);
             } else {
-              float anchor[3], axis[3];
-              rotq(t, C.jnt_pos[j], quat);
-              anchor[0] = t[0] + pos[0]; anchor[1] = t[1] + pos[1]; anchor[2] = t[2] + pos[2];
-              rotq(axis, C.jnt_axis[j], quat);
-              S.cdof[da][0] = axis[0]; S.cdof[da][1] = axis[1]; S.cdof[da][2] = axis[2];
-              S.cdof[da][3] = anchor[0]; S.cdof[da][4] = anchor[1]; S.cdof[da][5] = anchor[2];
-              float ang = S.vec[VQPOS][qa] - C.qpos0[qa], sn, cs;
-              sincosf(ang * 0.5f, &sn, &cs);
-              float ql[4] = {cs, C.jnt_axis[j][0] * sn, C.jnt_axis[j][1] * sn, C.jnt_axis[j][2] * sn}, qn[4];
-              quat_mul(qn, quat, ql);
-              quat[0] = qn[0]; quat[1] = qn[1]; quat[2] = qn[2]; quat[3] = qn[3];
-              rotq(t, C.jnt_pos[j], quat);
-              pos[0] = anchor[0] - t[0]; pos[1] = anchor[1] - t[1]; pos[2] = anchor[2] - t[2];
+              ep[0] = dp[0]; ep[1] = dp[1]; ep[2] = dp[2];
+              eq[0] = ql[0]; eq[1] = ql[1]; eq[2] = ql[2]; eq[3] = ql[3];
             }
           }
-          S.a.xpos[b][0] = pos[0]; S.a.xpos[b][1] = pos[1]; S.a.xpos[b][2] = pos[2];
-          S.a.xquat[b][0] = quat[0]; S.a.xquat[b][1] = quat[1]; S.a.xquat[b][2] = quat[2]; S.a.xquat[b][3] = quat[3];
+        }
+        for (int st = 0; st < C.tree_steps; st++) {
+          const int src = jp < 0 ? 0 : jp;
+          float P[3], Q[4];
+#pragma unroll
+          for (int k = 0; k < 3; k++) P[k] = __shfl_sync(FULL, ep[k], src);
+#pragma unroll
+          for (int k = 0; k < 4; k++) Q[k] = __shfl_sync(FULL, eq[k], src);
+          const int jp2 = __shfl_sync(FULL, jp, src);
+          if (jp >= 0) {
+            float t[3], qn[4];
+            rotq(t, ep, Q);
+            ep[0] = P[0] + t[0]; ep[1] = P[1] + t[1]; ep[2] = P[2] + t[2];
+            quat_mul(qn, Q, eq);
+            eq[0] = qn[0]; eq[1] = qn[1]; eq[2] = qn[2]; eq[3] = qn[3];
+            jp = jp2;
+          }
+        }
+        if (lane < C.njnt && C.jnt_type[lane] != 0) {  // hinge: stash world axis / anchor in its cdof slot (finalised after com)
+          const int da = C.jnt_dofadr[lane];
+          float t[3], axis[3];
+          rotq(t, C.jnt_pos[lane], eq);
+          rotq(axis, C.jnt_axis[lane], eq);
+          S.cdof[da][0] = axis[0]; S.cdof[da][1] = axis[1]; S.cdof[da][2] = axis[2];
+          S.cdof[da][3] = ep[0] + t[0]; S.cdof[da][4] = ep[1] + t[1]; S.cdof[da][5] = ep[2] + t[2];
+        }
+        {  // body frames: the frame after the body's last joint (or of the nearest jointed ancestor) composed with a fixed offset
+          const int sj = lane < nbody ? C.body_srcjnt[lane] : -1;
+          const int src = sj < 0 ? 0 : sj;
+          float P[3], Q[4];
+#pragma unroll
+          for (int k = 0; k < 3; k++) P[k] = __shfl_sync(FULL, ep[k], src);
+#pragma unroll
+          for (int k = 0; k < 4; k++) Q[k] = __shfl_sync(FULL, eq[k], src);
+          if (sj < 0) { P[0] = P[1] = P[2] = 0.0f; Q[0] = 1.0f; Q[1] = Q[2] = Q[3] = 0.0f; }
+          if (lane < nbody) {
+            float t[3], qn[4];
+            rotq(t, C.body_relpos[lane], Q);
+            quat_mul(qn, Q, C.body_relquat[lane]);
+            S.a.xpos[lane][0] = P[0] + t[0]; S.a.xpos[lane][1] = P[1] + t[1]; S.a.xpos[lane][2] = P[2] + t[2];
+            S.a.xquat[lane][0] = qn[0]; S.a.xquat[lane][1] = qn[1]; S.a.xquat[lane][2] = qn[2]; S.a.xquat[lane][3] = qn[3];
+          }
         }
         __syncwarp();
       }
@@ -671,50 +710,67 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
       }
       __syncwarp();
 
-      // ---------------------------------------------------------------- com_vel + cacc (root -> leaf), body-local cfrc
-      if (lane == 0) {
+      // ---------------------------------------------------------------- com_vel + cacc: two inclusive prefix sums over the dof tree
+      // cvel[b] = sum of cdof_d*qvel_d over the dofs moving b; cdof_dot_d = (cvel before dof d) x cdof_d; cacc[b] = -g + sum cdof_dot_d*qvel_d
+      // (mjx smooth.com_vel / rne forward pass; the free joint's angular dofs see the velocity after its three linear dofs only).
+      {
+        float I6[6], W6[6], cd[6] = {0, 0, 0, 0, 0, 0};
+        const float qv = (lane < NV) ? v : 0.0f;
+        if (lane < NV) {
 #pragma unroll
-        for (int k = 0; k < 6; k++) { S.a.cvel[0][k] = 0.0f; S.a.cacc[0][k] = 0.0f; }
-        S.a.cacc[0][3] = -C.gravity[0]; S.a.cacc[0][4] = -C.gravity[1]; S.a.cacc[0][5] = -C.gravity[2];
+          for (int k = 0; k < 6; k++) cd[k] = S.cdof[lane][k];
+        }
+#pragma unroll
+        for (int k = 0; k < 6; k++) I6[k] = cd[k] * qv;
+        int dp_ = lane < NV ? C.dof_parent[lane] : -1;
+        for (int st = 0; st < C.tree_steps; st++) {
+          const int src = dp_ < 0 ? 0 : dp_;
+          float g6[6];
+#pragma unroll
+          for (int k = 0; k < 6; k++) g6[k] = __shfl_sync(FULL, I6[k], src);
+          const int p2 = __shfl_sync(FULL, dp_, src);
+          if (dp_ >= 0) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) I6[k] += g6[k];
+            dp_ = p2;
+          }
+        }
+        const int cs_ = lane < NV ? C.dof_cvel_src[lane] : -2;
+        float cb[6];
+#pragma unroll
+        for (int k = 0; k < 6; k++) cb[k] = __shfl_sync(FULL, I6[k], cs_ < 0 ? 0 : cs_);
+        if (cs_ < 0) {
+#pragma unroll
+          for (int k = 0; k < 6; k++) cb[k] = 0.0f;
+        }
+        float cdd[6];
+        motion_cross(cdd, cb, cd);
+#pragma unroll
+        for (int k = 0; k < 6; k++) W6[k] = (cs_ == -2) ? 0.0f : cdd[k] * qv;
+        dp_ = lane < NV ? C.dof_parent[lane] : -1;
+        for (int st = 0; st < C.tree_steps; st++) {
+          const int src = dp_ < 0 ? 0 : dp_;
+          float g6[6];
+#pragma unroll
+          for (int k = 0; k < 6; k++) g6[k] = __shfl_sync(FULL, W6[k], src);
+          const int p2 = __shfl_sync(FULL, dp_, src);
+          if (dp_ >= 0) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) W6[k] += g6[k];
+            dp_ = p2;
+          }
+        }
+        const int ld = lane < nbody ? C.body_lastdof[lane] : -1;
+        float cv[6], ca[6];
+#pragma unroll
+        for (int k = 0; k < 6; k++) { cv[k] = __shfl_sync(FULL, I6[k], ld < 0 ? 0 : ld); ca[k] = __shfl_sync(FULL, W6[k], ld < 0 ? 0 : ld); }
+        if (lane < nbody) {
+#pragma unroll
+          for (int k = 0; k < 6; k++) { S.a.cvel[lane][k] = ld < 0 ? 0.0f : cv[k]; S.a.cacc[lane][k] = ld < 0 ? 0.0f : ca[k]; }
+          S.a.cacc[lane][3] -= C.gravity[0]; S.a.cacc[lane][4] -= C.gravity[1]; S.a.cacc[lane][5] -= C.gravity[2];
+        }
       }
       __syncwarp();
-      for (int lev = 1; lev <= C.maxdepth; lev++) {
-        if (lane < nbody && C.body_depth[lane] == lev) {
-          const int b = lane, p = C.body_parent[b];
-          float cv[6], ca[6], cdd[6];
-#pragma unroll
-          for (int k = 0; k < 6; k++) { cv[k] = S.a.cvel[p][k]; ca[k] = S.a.cacc[p][k]; }
-          for (int j = C.body_jntadr[b]; j < C.body_jntadr[b] + C.body_jntnum[b]; j++) {
-            const int da = C.jnt_dofadr[j];
-            if (C.jnt_type[j] == 0) {
-              for (int i = 0; i < 3; i++) {
-                float qv = S.vec[VQVEL][da + i];
-#pragma unroll
-                for (int k = 0; k < 6; k++) cv[k] += S.cdof[da + i][k] * qv;
-              }
-              for (int i = 3; i < 6; i++) {
-                float qv = S.vec[VQVEL][da + i];
-                motion_cross(cdd, cv, S.cdof[da + i]);
-#pragma unroll
-                for (int k = 0; k < 6; k++) ca[k] += cdd[k] * qv;
-              }
-              for (int i = 3; i < 6; i++) {
-                float qv = S.vec[VQVEL][da + i];
-#pragma unroll
-                for (int k = 0; k < 6; k++) cv[k] += S.cdof[da + i][k] * qv;
-              }
-            } else {
-              float qv = S.vec[VQVEL][da];
-              motion_cross(cdd, cv, S.cdof[da]);
-#pragma unroll
-              for (int k = 0; k < 6; k++) { ca[k] += cdd[k] * qv; cv[k] += S.cdof[da][k] * qv; }
-            }
-          }
-#pragma unroll
-          for (int k = 0; k < 6; k++) { S.a.cvel[b][k] = cv[k]; S.a.cacc[b][k] = ca[k]; }
-        }
-        __syncwarp();
-      }
       if (lane < nbody) {  // f = I*cacc + cvel x* (I*cvel), written over cacc[b]
         float ci[10], ca[6], cv[6], f1[6], iv[6], f2[6];
 #pragma unroll

@@ -25,8 +25,9 @@ def test_overflow_envs_match_oracle(model, oracle):
     assert ((status & 2) != 0)[ncand > 34].all() and ((status & 2) == 0)[ncand < 17].all()
     g = out["qacc"].double().cpu().numpy()
     rel = lambda a, b: np.abs(a - b) / np.maximum(1, np.abs(b))
-    eg, e32 = rel(g, ref["qacc"])[big], rel(r32["qacc"], ref["qacc"])[big]
-    assert eg.max() <= 3 * e32.max() + 1e-4
+    from test_gpu_parity import assert_f32_equivalent
+    eg, e32 = rel(g, ref["qacc"])[big].max(axis=1), rel(r32["qacc"], ref["qacc"])[big].max(axis=1)
+    assert_f32_equivalent(eg, e32, 1e-4, "qacc of overflowing envs")
     cand_g = out["efc_active"].cpu().numpy() & 1
     assert ((cand_g != (ref["efc_active"] & 1)).sum(axis=1)[big] <= 1).all()
     # and a second launch (counters were reset by the consuming pass) gives identical bits
