@@ -30,7 +30,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/ -> libmjxb.so with nvcc for sm_100a (cross-compiles without a GPU)."""
     csrc = os.path.join(_HERE, "csrc")
     inc = os.path.join(_HERE, "..", "include")
-    srcs = [os.path.join(csrc, f) for f in ("mjxb_abi.cu", "mjxb_device.cuh")] + [os.path.join(inc, f) for f in ("mjxb.h", "mjxb_model.h")]
+    srcs = [os.path.join(csrc, f) for f in ("mjxb_abi.cu", "mjxb_device.cuh", "mjxb_chol_tree.cuh")] + [os.path.join(inc, f) for f in ("mjxb.h", "mjxb_model.h")]
     stale = force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
     if stale:
         r = subprocess.run(["make", "-C", csrc, "-B", "../libmjxb.so"], capture_output=True, text=True)

@@ -113,6 +113,9 @@ int build_dev_model(const mjxb_model_blob& b, const mjxb_env_config* cfg, DevMod
   D.maxdepth = b.maxdepth;
   // exact line search whenever MJX's own search is run to convergence; the truncated settings keep MJX's iteration
   D.ls_exact = (b.ls_iterations >= 10) ? 1 : 0;
+  D.tree_chol_ok = (b.nv == kTreeNV) ? 1 : 0;
+  for (int d = 0; d < b.nv && d < kTreeNV; d++) if (b.dof_parent[d] != kTreeDofParent[d]) D.tree_chol_ok = 0;
+  if (getenv("MJXB_DENSE_CHOL")) D.tree_chol_ok = 0;
   if (getenv("MJXB_LS_ITERATIVE")) D.ls_exact = 0;
   D.timestep = b.timestep; D.tolerance = b.tolerance; D.ls_tolerance = b.ls_tolerance; D.meaninertia = b.meaninertia;
   for (int k = 0; k < 3; k++) D.gravity[k] = b.gravity[k];
@@ -249,6 +252,10 @@ int build_dev_model(const mjxb_model_blob& b, const mjxb_env_config* cfg, DevMod
   if (b.npair > MJXB_MAXPAIR || b.ncon > MAXCC_BIG || b.nefc > CAP_BIG) return MJXB_EUNSUPPORTED;
   for (int p = 0; p < b.npair; p++) {
     D.pair_w0[p] = (uint32_t)b.pair_g1[p] | ((uint32_t)b.pair_g2[p] << 8) | ((uint32_t)b.pair_kind[p] << 16) | ((uint32_t)b.pair_condim[p] << 24);
+    {  // bit 31: the two bodies sit on different limbs (neither dof chain contains the other): such a row breaks the tree pattern of H
+      const uint32_t m1 = D.body_dofmask[b.geom_body[b.pair_g1[p]]], m2 = D.body_dofmask[b.geom_body[b.pair_g2[p]]];
+      if ((m1 & m2) != m1 && (m1 & m2) != m2) D.pair_w0[p] |= 0x80000000u;
+    }
     D.pair_w1[p] = (uint32_t)b.pair_conadr[p] | ((uint32_t)b.pair_efcadr[p] << 16);
     pp[p].mu = b.pair_mu[p]; pp[p].invweight = b.pair_invweight[p];
     for (int k = 0; k < 2; k++) pp[p].solref[k] = b.pair_solref[p][k];

@@ -56,6 +56,7 @@ struct DevModel {
   float body_relpos[MJXB_MAXBODY][3], body_relquat[MJXB_MAXBODY][4];  // fixed offset of the body frame from that joint frame
   int dof_cvel_src[MJXB_MAXDOF];  // dof whose inclusive velocity prefix is 'cvel before this dof' (-1: zero, -2: cdof_dot = 0)
   int tree_steps;  // pointer-jumping rounds covering the deepest joint / dof chain
+  int tree_chol_ok;  // the model's dof tree is the one mjxb_chol_tree.cuh was generated for
   float jnt_pos[MJXB_MAXJNT][3], jnt_axis[MJXB_MAXJNT][3];
   int lim_dof[MJXB_MAXJNT], lim_qadr[MJXB_MAXJNT], lim_row[MJXB_MAXJNT];
   float lim_range[MJXB_MAXJNT][2], lim_invweight[MJXB_MAXJNT], lim_solref[MJXB_MAXJNT][2], lim_solimp[MJXB_MAXJNT][5];
@@ -409,6 +410,10 @@ __device__ __forceinline__ float chol_solve_rows(WS& S, int lane, const float (&
 }
 
 struct LSPoint { float alpha, cost, d0, d1; };
+
+}  // namespace mjxb
+#include "mjxb_chol_tree.cuh"
+namespace mjxb {
 
 // barrier over a group of `g` consecutive warps (named barrier 1 + group index); g <= 0 or g >= CTA: the whole CTA
 __device__ __forceinline__ void group_sync(int warp, int g) {
@@ -848,15 +853,17 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
 
       // ---------------------------------------------------------------- collision: lane per geom pair, candidates compacted by ballot
       int ncc = 0;
+      bool tree_ok = C.tree_chol_ok != 0;
       for (int base = 0; base < C.npair; base += 32) {
         const int p = base + lane;
         const bool valid = p < C.npair;
         float dist[2] = {1.0f, 1.0f}, cpos[2][3] = {{0, 0, 0}, {0, 0, 0}}, n[3] = {0, 0, 1}, t1[3] = {0, 0, 0}, t2[3] = {0, 0, 0};
         int kind = -1, condim = 1;
+        bool cross_branch = false;
         if (valid) {
           const uint32_t w0 = C.pair_w0[p];
           const int g1 = w0 & 0xff, g2 = (w0 >> 8) & 0xff;
-          kind = (w0 >> 16) & 0xff; condim = (w0 >> 24) & 0xff;
+          kind = (w0 >> 16) & 0xff; condim = (w0 >> 24) & 0x7f; cross_branch = (w0 >> 31) != 0u;
           float p1[3] = {S.gpos[g1][0], S.gpos[g1][1], S.gpos[g1][2]}, p2[3] = {S.gpos[g2][0], S.gpos[g2][1], S.gpos[g2][2]};
           float ax1[3] = {S.gaxis[g1][0], S.gaxis[g1][1], S.gaxis[g1][2]}, ax2[3] = {S.gaxis[g2][0], S.gaxis[g2][1], S.gaxis[g2][2]};
           const float r1 = C.geom_rad[g1], r2 = C.geom_rad[g2], l1 = C.geom_half[g1], l2 = C.geom_half[g2];
@@ -920,6 +927,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
         for (int e = 0; e < 2; e++) {
           const bool cand = valid && (e == 0 || kind == PAIR_PLANE_CAPSULE) && dist[e] < 0.0f;
           const unsigned mk = __ballot_sync(FULL, cand);
+          if (__ballot_sync(FULL, cand && cross_branch) != 0u) tree_ok = false;  // a row will couple two limbs: dense factorisation
           const int idx = ncc + __popc(mk & lt_mask);
           if (cand && idx < MAXCC) {
 #pragma unroll
@@ -1163,9 +1171,14 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
           for (int j = 0; j < NVP; j++) a[j] = 0.0f;
         }
         const float rhs = (phase == 0) ? qfs : (phase == 1) ? grad : (qfs + qfc);
-        float dinv;
-        chol_rows(S, lane, a, dinv);
-        const float x = chol_solve_rows(S, lane, a, dinv, (lane < NV) ? rhs : 0.0f);
+        float dinv, x;
+        if (tree_ok || (phase != 1 && C.tree_chol_ok != 0)) {  // M and M + h*damping always follow the tree pattern; H does unless a row couples two limbs
+          chol_tree(S, lane, a, dinv);
+          x = chol_tree_solve(S, lane, a, dinv, (lane < NV) ? rhs : 0.0f);
+        } else {
+          chol_rows(S, lane, a, dinv);
+          x = chol_solve_rows(S, lane, a, dinv, (lane < NV) ? rhs : 0.0f);
+        }
 
         if (phase == 0) {
           qas = x;
