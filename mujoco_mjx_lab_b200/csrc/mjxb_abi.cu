@@ -14,6 +14,7 @@ using namespace mjxb;
 
 namespace {
 
+constexpr int kResetPad = 148 * 16 * 2;  // per-CTA reset queues are sized in whole rounds: n_env + (CTAs x warps) entries at most
 thread_local char g_cuda_err[512] = "";
 
 int cuda_fail(cudaError_t e, const char* what) {
@@ -93,7 +94,7 @@ int arena_ensure(mjxb_model* m, int n) {
   a.chunk = (n + nchunk - 1) / nchunk;
   for (int i = 0; i < Arena::kSlots; i++) {
     CU(cudaStreamCreateWithFlags(&a.pipe[i], cudaStreamNonBlocking));
-    CU(cudaMalloc(&a.pipe_ovf[i], (2 * (size_t)a.chunk + 4) * sizeof(int)));
+    CU(cudaMalloc(&a.pipe_ovf[i], (3 * (size_t)a.chunk + 4 + kResetPad) * sizeof(int)));
     CU(cudaMemsetAsync(a.pipe_ovf[i], 0, 4 * sizeof(int), a.stream));
   }
   CU(cudaStreamSynchronize(a.stream));
@@ -300,7 +301,7 @@ int launch(const mjxb_model* mc, const StepArgs& args_in, bool dbg, cudaStream_t
   if (cur != m->device) CU(cudaSetDevice(m->device));
   if (ovf_buf == nullptr && m->ovf_cap < args_in.n_env) {
     if (m->ovf) { CU(cudaStreamSynchronize(stream)); CU(cudaFree(m->ovf)); m->ovf = nullptr; }
-    CU(cudaMalloc(&m->ovf, (2 * (size_t)args_in.n_env + 4) * sizeof(int)));
+    CU(cudaMalloc(&m->ovf, (3 * (size_t)args_in.n_env + 4 + kResetPad) * sizeof(int)));
     CU(cudaMemsetAsync(m->ovf, 0, 4 * sizeof(int), stream));
     m->ovf_cap = args_in.n_env;
   }
@@ -310,6 +311,7 @@ int launch(const mjxb_model* mc, const StepArgs& args_in, bool dbg, cudaStream_t
   int* listA = ovf + 4;
   int* listB = ovf + 4 + cap;
   args.in_count = nullptr; args.in_list = nullptr; args.in_done = nullptr; args.out_count = ovf; args.out_list = listA;
+  args.reset_list = (getenv("MJXB_INLINE_RESET") != nullptr) ? nullptr : ovf + 4 + 2 * (size_t)cap;
   { const char* e = getenv("MJXB_LOCKSTEP"); args.lockstep = e ? atoi(e) : 1; }  // default on; MJXB_LOCKSTEP=0 disables (profiling aid)
   { const char* e = getenv("MJXB_LOCKSTEP_GROUP"); args.lockstep_group = e ? atoi(e) : 0; }
   // small batches: spread the envs over every SM (fewer warps per CTA run faster than 16 sharing one SM's issue slots)
@@ -319,6 +321,7 @@ int launch(const mjxb_model* mc, const StepArgs& args_in, bool dbg, cudaStream_t
   int grid = (args.n_env + warps - 1) / warps;
   if (grid > m->num_sms) grid = m->num_sms;
   const size_t smem_main = m->smem - (size_t)(m->warps - warps) * sizeof(WarpS<CAP_MAIN, MAXCC_MAIN>);
+  args.reset_stride = ((args.n_env + grid * warps - 1) / (grid * warps)) * warps;
   const bool ls = m->host.ls_exact != 0 && m->host.solver == 2;  // fast instantiation: Newton + exact line search; else the general one
 #define MJXB_LAUNCH(CAPv, CCv, Wv, G, B, SM)                                                                                   \
   do {                                                                                                                        \
@@ -334,6 +337,7 @@ int launch(const mjxb_model* mc, const StepArgs& args_in, bool dbg, cudaStream_t
     const int wm = m->warps_mid;
     int gridm = m->num_sms;
     if (gridm * wm > args.n_env) gridm = (args.n_env + wm - 1) / wm;
+    args.reset_stride = ((args.n_env + gridm * wm - 1) / (gridm * wm)) * wm;
     MJXB_LAUNCH(CAP_MID, MAXCC_MID, WARPS_MID, gridm, wm * 32, m->smem_mid);
     e = cudaGetLastError();
   }
@@ -342,6 +346,7 @@ int launch(const mjxb_model* mc, const StepArgs& args_in, bool dbg, cudaStream_t
     const int wb = m->warps_big;
     int gridb = m->num_sms;
     if (gridb * wb > args.n_env) gridb = (args.n_env + wb - 1) / wb;
+    args.reset_stride = ((args.n_env + gridb * wb - 1) / (gridb * wb)) * wb;
     MJXB_LAUNCH(CAP_BIG, MAXCC_BIG, WARPS_BIG, gridb, wb * 32, m->smem_big);
 #undef MJXB_LAUNCH
     e = cudaGetLastError();
@@ -449,7 +454,7 @@ int mjxb_model_dims(const mjxb_model* m, int32_t dims[8]) {
   return MJXB_OK;
 }
 
-size_t mjxb_model_scratch_bytes(const mjxb_model* m) { return m ? (2 * (size_t)m->ovf_cap + 4) * sizeof(int) : 0; }
+size_t mjxb_model_scratch_bytes(const mjxb_model* m) { return m ? (3 * (size_t)m->ovf_cap + 4 + kResetPad) * sizeof(int) : 0; }
 
 int mjxb_launch_config(const mjxb_model* m, int32_t cfg[4]) {  // warps per CTA, dynamic smem bytes, SM count, sizeof(WarpS)
   if (!m || !cfg) return MJXB_EINVAL;

@@ -92,6 +92,9 @@ struct StepArgs {
   // row tile cannot hold to `out_list` (NULL: none -- the last tier holds every static row), and resets its input list when done
   int* in_count; int* in_list; int* in_done;
   int* out_count; int* out_list;
+  // deferred auto-reset: envs that finish an episode are queued per CTA and re-initialised in packed lockstep rounds after the
+  // step rounds (a reset run inline would make the other 15 warps of its round wait for a whole extra pass)
+  int* reset_list; int reset_stride;
   int lockstep;          // CTA barriers keep the warps of an SM in the same code region (instruction-cache locality)
   int lockstep_group;    // warps per barrier group (0 = the whole CTA)
   mjxb_debug dbg;
@@ -435,6 +438,8 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
     int4* dst = reinterpret_cast<int4*>(smem_raw);
     for (int i = threadIdx.x; i < (int)(sizeof(DevModel) / 16); i += blockDim.x) dst[i] = src[i];
   }
+  __shared__ int s_reset_count;
+  if (threadIdx.x == 0) s_reset_count = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   using WS = WarpS<CAP, MAXCC>;
@@ -448,16 +453,35 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
   const bool consuming = A.in_list != nullptr;
   const int n_items = consuming ? *reinterpret_cast<volatile int*>(A.in_count) : A.n_env;
   const int n_rounds = (n_items + gridDim.x * nwarp - 1) / (gridDim.x * nwarp);
-  for (int round = 0; round < n_rounds; round++) {
+  const bool defer = A.autoreset && A.reset_list != nullptr && A.mode == MODE_ENV_STEP;
+  int total_rounds = n_rounds, n_reset = 0;
+  bool reset_phase = false;
+  for (int round = 0;; round++) {
+    if (round == total_rounds) {  // CTA-uniform: after the step rounds, the queued resets run 16 per round
+      if (reset_phase || !defer) break;
+      __syncthreads();
+      n_reset = s_reset_count;
+      reset_phase = true;
+      total_rounds += (n_reset + nwarp - 1) / nwarp;
+      if (round == total_rounds) break;
+    }
     if (A.lockstep > 0) group_sync(warp, A.lockstep_group);
-    const int item = (round * gridDim.x + blockIdx.x) * nwarp + warp;
     // Warps without work in the last round (and envs that overflow the row tile) still run the whole pipeline -- on env 0 /
     // on a truncated row set -- with every global store suppressed, so that all warps of the CTA reach the same barriers.
-    const bool valid = item < n_items;
-    const int env = valid ? (consuming ? A.in_list[item] : item) : (consuming ? A.in_list[0] : 0);
-    bool overflow = false;
+    bool valid;
+    int env;
+    if (!reset_phase) {
+      const int item = (round * gridDim.x + blockIdx.x) * nwarp + warp;
+      valid = item < n_items;
+      env = valid ? (consuming ? A.in_list[item] : item) : (consuming ? A.in_list[0] : 0);
+    } else {
+      const int idx = (round - n_rounds) * nwarp + warp;
+      valid = idx < n_reset;
+      env = A.reset_list[(size_t)blockIdx.x * A.reset_stride + (valid ? idx : 0)];
+    }
+    bool overflow = false, deferred = false;
     // ---------------------------------------------------------------- load state (lane d <-> qpos[d], qvel[d], ...)
-    int mode = A.mode;
+    int mode = reset_phase ? MODE_ENV_RESET : A.mode;
     float q = 0.0f, v = 0.0f, ws = 0.0f, ctrl = 0.0f, tm = 0.0f, aux = 0.0f, action = 0.0f;
     int status = consuming ? MJXB_STATUS_ROW_SPILL : 0;
     if (mode == MODE_ENV_STEP || mode == MODE_PHYS_STEP || mode == MODE_FORWARD) {
@@ -1516,10 +1540,14 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
         if (lane == 7) aux = last_pot; if (lane == 8) aux = ep;
 
         const bool done_env = (mode == MODE_ENV_STEP) && (fmaxf(out_term, out_trunc) > 0.0f);
-        if (done_env && A.autoreset) {  // train_ppo.py:150-161 fused: re-run the pipeline in reset mode for this env
-          mode = MODE_ENV_RESET;
+        if (done_env && A.autoreset) {  // train_ppo.py:150-161 fused
           did_reset = 1;
-          continue;
+          if (defer) {
+            deferred = true;             // queued below; the reset phase of this launch re-initialises it
+          } else {
+            mode = MODE_ENV_RESET;       // inline: re-run the pipeline in reset mode for this env
+            continue;
+          }
         }
         // observation (src/envs.py:274-331): [height, rpy, qpos[7:], R^T v_lin, R^T v_ang, qvel[6:], tgt]
         const float angle = atan2f(dyo, dxo) - yaw;
@@ -1545,7 +1573,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
           } else if (src < 4 + nqj + C.nv) val = S.vec[VQVEL][6 + (src - 4 - nqj - 6)];
           else val = (src == od - 2) ? tg0 : tg1;
           if (flip > 0.5f) val *= cfg.obs_sign[o];
-          if (valid && !overflow) A.obs[(size_t)env * od + o] = val;
+          if (valid && !overflow && !deferred) A.obs[(size_t)env * od + o] = val;
         }
       }
       break;
@@ -1564,6 +1592,17 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
     }
 
     // ------------------------------------------------------------------ store
+    if (deferred) {  // step results now, state / obs / aux from the reset phase
+      if (lane == 0) {
+        A.reward[env] = out_reward; A.terminated[env] = out_term; A.truncated[env] = out_trunc;
+        if (A.reset_mask) A.reset_mask[env] = 1;
+        if (A.status) A.status[env] = status;
+        const int slot = atomicAdd(&s_reset_count, 1);
+        A.reset_list[(size_t)blockIdx.x * A.reset_stride + slot] = env;
+      }
+      __syncwarp();
+      continue;
+    }
     if (A.mode == MODE_SPEED_TEST) {
       if (lane == 0) A.pos[env] = q;
     } else {
@@ -1573,12 +1612,12 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
       if (A.mode == MODE_ENV_STEP || A.mode == MODE_ENV_RESET) {
         if (lane < MJXB_AUX_DIM) A.out.aux[(size_t)env * MJXB_AUX_DIM + lane] = aux;
       }
-      if (A.mode == MODE_ENV_STEP && lane == 0) {
+      if (A.mode == MODE_ENV_STEP && !reset_phase && lane == 0) {
         A.reward[env] = out_reward; A.terminated[env] = out_term; A.truncated[env] = out_trunc;
         if (A.reset_mask) A.reset_mask[env] = (uint8_t)did_reset;
       }
     }
-    if (A.status && lane == 0) A.status[env] = status;
+    if (A.status && lane == 0) A.status[env] = reset_phase ? (A.status[env] | status) : status;
     __syncwarp();
   }
   if (consuming) {  // last CTA out resets the consumed list's counters for the next step
