@@ -127,6 +127,7 @@ struct __align__(16) WarpS {
   int cc_pair[MAXCC], cc_row[MAXCC];
   float site_xpos[MJXB_MAXSITE][3], site_xmat[MJXB_MAXSITE][9];
   float pelvis_pos[3], pelvis_quat[4], head_pos[3];
+  float sens[MJXB_MAXSENSOR];
   float pad_[2];
 };
 
@@ -194,7 +195,7 @@ __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fm
 
 // ------------------------------------------------------------------------------------------- threefry / jax.random
 __device__ __forceinline__ uint32_t rotl32(uint32_t v, int r) { return (v << r) | (v >> (32 - r)); }
-__device__ __noinline__ void threefry2x32(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t& o0, uint32_t& o1) {
+__device__ __noinline__ uint2 threefry2x32v(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1) {  // by value: reference outputs would force the callers' locals into local memory
   uint32_t ks0 = k0, ks1 = k1, ks2 = k0 ^ k1 ^ 0x1BD11BDAu;
   uint32_t x0 = c0 + ks0, x1 = c1 + ks1;
 #define MJXB_TF_R(r) { x0 += x1; x1 = rotl32(x1, r); x1 ^= x0; }
@@ -204,7 +205,11 @@ __device__ __noinline__ void threefry2x32(uint32_t k0, uint32_t k1, uint32_t c0,
   MJXB_TF_R(17) MJXB_TF_R(29) MJXB_TF_R(16) MJXB_TF_R(24) x0 += ks1; x1 += ks2 + 4u;
   MJXB_TF_R(13) MJXB_TF_R(15) MJXB_TF_R(26) MJXB_TF_R(6)  x0 += ks2; x1 += ks0 + 5u;
 #undef MJXB_TF_R
-  o0 = x0; o1 = x1;
+  return make_uint2(x0, x1);
+}
+__device__ __forceinline__ void threefry2x32(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t& o0, uint32_t& o1) {
+  const uint2 r = threefry2x32v(k0, k1, c0, c1);
+  o0 = r.x; o1 = r.y;
 }
 // jax.random.uniform(key, (n,), f32, minval, maxval)[i] with threefry_partitionable
 __device__ __forceinline__ float jax_uniform(uint32_t k0, uint32_t k1, uint32_t i, float minval, float maxval) {
@@ -215,9 +220,8 @@ __device__ __forceinline__ float jax_uniform(uint32_t k0, uint32_t k1, uint32_t 
 }
 
 // ------------------------------------------------------------------------------------------- constraint impedance (mjx constraint._kbi)
-__device__ __noinline__ void kbi_general_power(float mid, float power, float x, float& ia, float& ib) {  // cold: solimp power not in {1, 2}
-  ia = (1.0f / powf(mid, power - 1.0f)) * powf(x, power);
-  ib = 1.0f - (1.0f / powf(1.0f - mid, power - 1.0f)) * powf(1.0f - x, power);
+__device__ __noinline__ float2 kbi_general_power(float mid, float power, float x) {  // cold: solimp power not in {1, 2}
+  return make_float2((1.0f / powf(mid, power - 1.0f)) * powf(x, power), 1.0f - (1.0f / powf(1.0f - mid, power - 1.0f)) * powf(1.0f - x, power));
 }
 __device__ __forceinline__ void kbi(float timestep, const float* solref, const float* solimp, float pos, float& k, float& b, float& imp) {
   float timeconst = fmaxf(solref[0], 2.0f * timestep), dampratio = solref[1];
@@ -231,7 +235,7 @@ __device__ __forceinline__ void kbi(float timestep, const float* solref, const f
   float ia, ib;
   if (power == 2.0f) { ia = (1.0f / mid) * (x * x); ib = 1.0f - (1.0f / (1.0f - mid)) * ((1.0f - x) * (1.0f - x)); }
   else if (power == 1.0f) { ia = x; ib = x; }
-  else { kbi_general_power(mid, power, x, ia, ib); }
+  else { const float2 r = kbi_general_power(mid, power, x); ia = r.x; ib = r.y; }
   float y = x < mid ? ia : ib;
   imp = clampf(dmin + y * (dmax - dmin), dmin, dmax);
   if (x > 1.0f) imp = dmax;
@@ -291,22 +295,26 @@ __device__ __forceinline__ void make_tangents(const float* n, float* t1, float* 
   t1[0] = b[0]; t1[1] = b[1]; t1[2] = b[2];
   cross3(t2, n, b);
 }
-// nearest x >= 0 with pnt + x*vec on a face of the axis-aligned box `size`, else -1 (engine_ray.c ray_box / mjx ray._ray_box)
-__device__ __noinline__ float ray_box(const float* size, const float* pnt, const float* vec) {
-  float best = -1.0f;
-#pragma unroll
-  for (int i = 0; i < 3; i++) {
-    const int i0 = (i == 0) ? 1 : 0, i1 = (i == 2) ? 1 : 2;
-    if (fabsf(vec[i]) <= MINVAL) continue;
+// nearest x >= 0 with pnt + x*vec on a face of the axis-aligned box `size`, else -1 (engine_ray.c ray_box / mjx ray._ray_box).
+// One face pair; everything by value so that nothing is forced into local memory.
+__device__ __forceinline__ float ray_box_axis(float best, float s_i, float p_i, float v_i, float s_a, float p_a, float v_a, float s_b, float p_b, float v_b) {
+  if (fabsf(v_i) > MINVAL) {
 #pragma unroll
     for (int side = -1; side <= 1; side += 2) {
-      float sol = ((float)side * size[i] - pnt[i]) / vec[i];
+      const float sol = ((float)side * s_i - p_i) / v_i;
       if (sol >= 0.0f) {
-        float p0 = pnt[i0] + sol * vec[i0], p1 = pnt[i1] + sol * vec[i1];
-        if (fabsf(p0) <= size[i0] && fabsf(p1) <= size[i1] && (best < 0.0f || sol < best)) best = sol;
+        const float qa = p_a + sol * v_a, qb = p_b + sol * v_b;
+        if (fabsf(qa) <= s_a && fabsf(qb) <= s_b && (best < 0.0f || sol < best)) best = sol;
       }
     }
   }
+  return best;
+}
+__device__ __forceinline__ float ray_box(float sx, float sy, float sz, float px, float py, float pz, float vx, float vy, float vz) {
+  float best = -1.0f;
+  best = ray_box_axis(best, sx, px, vx, sy, py, vy, sz, pz, vz);
+  best = ray_box_axis(best, sy, py, vy, sx, px, vx, sz, pz, vz);
+  best = ray_box_axis(best, sz, pz, vz, sx, px, vx, sy, py, vy);
   return best;
 }
 
@@ -482,30 +490,31 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
     bool overflow = false, deferred = false;
     // ---------------------------------------------------------------- load state (lane d <-> qpos[d], qvel[d], ...)
     int mode = reset_phase ? MODE_ENV_RESET : A.mode;
-    float q = 0.0f, v = 0.0f, ws = 0.0f, ctrl = 0.0f, tm = 0.0f, aux = 0.0f, action = 0.0f;
+    // Per-env values are NOT carried in registers across the pipeline (128 registers per thread, and the 24 KB of L1 left beside
+    // 230 KB of shared memory cannot hold spills): they are published to shared memory here and re-read where they are used.
+    float q = 0.0f, v = 0.0f, ws = 0.0f, ctrl = 0.0f, tm = 0.0f, aux = 0.0f;
     int status = consuming ? MJXB_STATUS_ROW_SPILL : 0;
-    if (mode == MODE_ENV_STEP || mode == MODE_PHYS_STEP || mode == MODE_FORWARD) {
-      if (lane < C.nq) q = A.in.qpos[(size_t)env * C.nq + lane];
-      if (lane < NV) { v = A.in.qvel[(size_t)env * NV + lane]; ws = A.in.qacc_warmstart[(size_t)env * NV + lane]; }
-      tm = A.in.time[env];
-      if (A.action != nullptr && lane < C.nu) action = A.action[(size_t)env * C.nu + lane];
+    {
+      float action = 0.0f;
+      if (mode == MODE_ENV_STEP || mode == MODE_PHYS_STEP || mode == MODE_FORWARD) {
+        if (lane < C.nq) q = A.in.qpos[(size_t)env * C.nq + lane];
+        if (lane < NV) { v = A.in.qvel[(size_t)env * NV + lane]; ws = A.in.qacc_warmstart[(size_t)env * NV + lane]; }
+        tm = A.in.time[env];
+        if (A.action != nullptr && lane < C.nu) action = A.action[(size_t)env * C.nu + lane];
+      }
+      if (mode == MODE_ENV_STEP) {
+        const float flip = A.in.aux[(size_t)env * MJXB_AUX_DIM];
+        // src/envs.py:339-341 flip + clip
+        int src = lane < C.nu ? cfg.act_perm[lane] : 0;
+        float af = __shfl_sync(FULL, action, src) * (lane < C.nu ? cfg.act_sign[lane] : 0.0f);
+        ctrl = clampf(flip > 0.5f ? af : action, -1.0f, 1.0f);
+      } else {
+        ctrl = action;
+      }
     }
-    if (mode == MODE_ENV_STEP) {
-      if (lane < MJXB_AUX_DIM) aux = A.in.aux[(size_t)env * MJXB_AUX_DIM + lane];
-      float flip = __shfl_sync(FULL, aux, 0);
-      // src/envs.py:339-341 flip + clip
-      int src = lane < C.nu ? cfg.act_perm[lane] : 0;
-      float af = __shfl_sync(FULL, action, src) * (lane < C.nu ? cfg.act_sign[lane] : 0.0f);
-      ctrl = clampf(flip > 0.5f ? af : action, -1.0f, 1.0f);
-    } else {
-      ctrl = action;
-    }
-    uint32_t key0 = 0, key1 = 0;
-    if (A.keys != nullptr) { key0 = A.keys[2 * (size_t)env]; key1 = A.keys[2 * (size_t)env + 1]; }
     // env-step outputs latched before an in-kernel auto-reset overwrites the state
     float out_reward = 0.0f, out_term = 0.0f, out_trunc = 0.0f;
-    float qfrc_act = 0.0f;
-    float tgt_x = 0.0f, tgt_y = 0.0f, tgt_z = 0.0f, flip_r = 0.0f;
+    float tgt_x = 0.0f, tgt_y = 0.0f, tgt_z = 0.0f, flip_r = 0.0f, vmag_r = 0.0f;
     int did_reset = 0;
 
     for (int istep = 0; istep < A.nsteps; istep++) {
@@ -517,6 +526,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
       for (int pass = 0; pass < 2; pass++) {  // pass 1 only for the fused auto-reset (no CTA barriers there)
       if (mode == MODE_ENV_RESET) {
         // ------------------------------------------------------------ single_reset state init (src/envs.py:117-131,147)
+        const uint32_t key0 = A.keys[2 * (size_t)env], key1 = A.keys[2 * (size_t)env + 1];
         uint32_t k1a, k1b, k2a, k2b, k3a, k3b, k4a, k4b;
         threefry2x32(key0, key1, 0u, 0u, k1a, k1b);
         threefry2x32(key0, key1, 0u, 1u, k2a, k2b);
@@ -537,8 +547,8 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
         if (cfg.initial_velocity_max > 0.0f) {
           // target = pelvis + (target_dist, 0): direction is +x up to rounding; vx = vmag*dx/|dx|, vy = vmag*0/|dx|
           float vmag = jax_uniform(k4a, k4b, 0u, 0.0f, cfg.initial_velocity_max);
-          // dx = (bx + target_dist) - bx is evaluated after kinematics below (needs pelvis x); stash vmag in `action`
-          action = vmag;
+          // dx = (bx + target_dist) - bx is evaluated after kinematics below (needs pelvis x)
+          vmag_r = vmag;
         }
         ws = 0.0f; ctrl = 0.0f; tm = 0.0f;
       }
@@ -546,7 +556,8 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
       __syncwarp();
       S.vec[VQPOS][lane] = q;
       S.vec[VQVEL][lane] = (lane < NV) ? v : 0.0f;
-      S.vec[VCTRL][lane] = ctrl;
+      S.vec[VX][lane] = (lane < NV) ? ws : 0.0f;   // warm start, read back by the solver (VX is scratch from the solver on)
+      if (istep == 0 || mode == MODE_ENV_RESET) S.vec[VCTRL][lane] = ctrl;  // constant over the in-kernel steps
       __syncwarp();
 
       // ---------------------------------------------------------------- kinematics: parallel prefix over the joint tree
@@ -627,20 +638,18 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
         }
         __syncwarp();
       }
-      q = S.vec[VQPOS][lane];  // kinematics normalised the free-joint quaternion in place
 
       if (mode == MODE_ENV_RESET && cfg.initial_velocity_max > 0.0f) {  // src/envs.py:136-152
         float bx = S.a.xpos[cfg.pelvis_body_id][0], by = S.a.xpos[cfg.pelvis_body_id][1];
         float tx = bx + cfg.target_dist, ty = by;
         float dx = tx - bx, dy = ty - by;
         float dist_xy = sqrtf(dx * dx + dy * dy);
-        float vmag = action;
+        float vmag = vmag_r;
         float vx = dist_xy > 1e-6f ? __fdiv_rn(__fmul_rn(vmag, dx), dist_xy) : 0.0f;
         float vy = dist_xy > 1e-6f ? __fdiv_rn(__fmul_rn(vmag, dy), dist_xy) : 0.0f;
-        if (lane == 0) v = vx;
-        if (lane == 1) v = vy;
         __syncwarp();
-        S.vec[VQVEL][lane] = (lane < NV) ? v : 0.0f;
+        if (lane == 0) S.vec[VQVEL][0] = vx;
+        if (lane == 1) S.vec[VQVEL][1] = vy;
         __syncwarp();
       }
 
@@ -744,7 +753,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
       // (mjx smooth.com_vel / rne forward pass; the free joint's angular dofs see the velocity after its three linear dofs only).
       {
         float I6[6], W6[6], cd[6] = {0, 0, 0, 0, 0, 0};
-        const float qv = (lane < NV) ? v : 0.0f;
+        const float qv = S.vec[VQVEL][lane];
         if (lane < NV) {
 #pragma unroll
           for (int k = 0; k < 6; k++) cd[k] = S.cdof[lane][k];
@@ -859,8 +868,8 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
         for (int k = 0; k < 6; k++) bias += cd[k] * cf[k];
         float passive = 0.0f;
         const int qa = C.dof_qadr[lane];
-        if (qa >= 0) passive = -C.dof_stiffness[lane] * (S.vec[VQPOS][qa] - C.qpos_spring[qa]) - C.dof_damping[lane] * v;
-        qfrc_act = 0.0f;
+        if (qa >= 0) passive = -C.dof_stiffness[lane] * (S.vec[VQPOS][qa] - C.qpos_spring[qa]) - C.dof_damping[lane] * S.vec[VQVEL][lane];
+        float qfrc_act = 0.0f;
         const int u = C.dof_act[lane];
         if (u >= 0) qfrc_act = C.dof_gear[lane] * clampf(S.vec[VCTRL][u], C.dof_ctrl_lo[lane], C.dof_ctrl_hi[lane]);
         qfs = passive - bias + qfrc_act;
@@ -1208,15 +1217,16 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
           qas = x;
           if (DBG && A.dbg.qacc_smooth && lane < NV) A.dbg.qacc_smooth[(size_t)env * NV + lane] = qas;
           // warm start (mjx solver.solve): cheaper of qacc_warmstart and qacc_smooth
-          float Ma_w = matvec_M(S, lane, ws);
-          rows_times(S, lane, nrow, ws, S.rjv);  // J*warm
+          const float w0 = S.vec[VX][lane];  // qacc_warmstart (parked at the top of the pass)
+          float Ma_w = matvec_M(S, lane, w0);
+          rows_times(S, lane, nrow, w0, S.rjv);  // J*warm
           float cs = 0.0f;
           for (int r = lane; r < nrow; r += 32) {
             float ja = S.rjv[r] - S.raref[r];
             S.rjv[r] = ja;
             cs += ja < 0.0f ? S.rD[r] * ja * ja : 0.0f;
           }
-          float cost_w = 0.5f * warp_sum(cs) + 0.5f * warp_sum((lane < NV) ? (Ma_w - qfs) * (ws - qas) : 0.0f);
+          float cost_w = 0.5f * warp_sum(cs) + 0.5f * warp_sum((lane < NV) ? (Ma_w - qfs) * (w0 - qas) : 0.0f);
           float Ma_s = matvec_M(S, lane, qas);
           rows_times(S, lane, nrow, qas, S.rJaref);
           cs = 0.0f;
@@ -1227,7 +1237,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
           }
           float cost_s = 0.5f * warp_sum(cs) + 0.5f * warp_sum((lane < NV) ? (Ma_s - qfs) * (qas - qas) : 0.0f);
           const bool use_warm = cost_w < cost_s;
-          qacc = use_warm ? ws : qas;
+          qacc = use_warm ? w0 : qas;
           Ma = use_warm ? Ma_w : Ma_s;
           if (use_warm) for (int r = lane; r < nrow; r += 32) S.rJaref[r] = S.rjv[r];
           __syncwarp();
@@ -1398,9 +1408,6 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
       }
 
       // ---------------------------------------------------------------- touch sensors (mjx sensor.sensor_acc / engine_sensor.c mjSENS_TOUCH)
-      float sens[MJXB_MAXSENSOR];
-#pragma unroll
-      for (int s = 0; s < MJXB_MAXSENSOR; s++) sens[s] = 0.0f;
       {
         float nf = 0.0f;
         int b1 = -1, b2 = -1;
@@ -1411,33 +1418,28 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
           nf = S.rforce[rb];
           if ((pr >> 20) > 1) nf = ((S.rforce[rb] + S.rforce[rb + 1]) + S.rforce[rb + 2]) + S.rforce[rb + 3];
         }
-#pragma unroll
-        for (int s = 0; s < MJXB_MAXSENSOR; s++) {
+#pragma unroll 1
+        for (int s = 0; s < C.nsensor; s++) {
           float contrib = 0.0f;
-          if (s < C.nsensor && lane < ncc && nf > 0.0f) {
-            const int site = C.sensor_site[s], sb = C.site_body[site];
-            if (sb == b1 || sb == b2) {
-              float ray[3] = {S.cc_n[lane][0] * nf, S.cc_n[lane][1] * nf, S.cc_n[lane][2] * nf};
-              normalize3(ray);
-              if (sb == b2) { ray[0] = -ray[0]; ray[1] = -ray[1]; ray[2] = -ray[2]; }
-              float dp[3] = {S.cc_pos[lane][0] - S.site_xpos[site][0], S.cc_pos[lane][1] - S.site_xpos[site][1],
-                             S.cc_pos[lane][2] - S.site_xpos[site][2]};
-              const float* Rm = S.site_xmat[site];
-              float lp[3] = {Rm[0] * dp[0] + Rm[3] * dp[1] + Rm[6] * dp[2], Rm[1] * dp[0] + Rm[4] * dp[1] + Rm[7] * dp[2],
-                             Rm[2] * dp[0] + Rm[5] * dp[1] + Rm[8] * dp[2]};
-              float lv[3] = {Rm[0] * ray[0] + Rm[3] * ray[1] + Rm[6] * ray[2], Rm[1] * ray[0] + Rm[4] * ray[1] + Rm[7] * ray[2],
-                             Rm[2] * ray[0] + Rm[5] * ray[1] + Rm[8] * ray[2]};
-              if (ray_box(C.site_size[site], lp, lv) >= 0.0f) contrib = nf;
-            }
+          const int site = C.sensor_site[s], sb = C.site_body[site];
+          if (lane < ncc && nf > 0.0f && (sb == b1 || sb == b2)) {
+            float ray[3] = {S.cc_n[lane][0] * nf, S.cc_n[lane][1] * nf, S.cc_n[lane][2] * nf};
+            normalize3(ray);
+            if (sb == b2) { ray[0] = -ray[0]; ray[1] = -ray[1]; ray[2] = -ray[2]; }
+            const float dx = S.cc_pos[lane][0] - S.site_xpos[site][0], dy = S.cc_pos[lane][1] - S.site_xpos[site][1],
+                        dz = S.cc_pos[lane][2] - S.site_xpos[site][2];
+            const float* Rm = S.site_xmat[site];
+            const float lpx = Rm[0] * dx + Rm[3] * dy + Rm[6] * dz, lpy = Rm[1] * dx + Rm[4] * dy + Rm[7] * dz,
+                        lpz = Rm[2] * dx + Rm[5] * dy + Rm[8] * dz;
+            const float lvx = Rm[0] * ray[0] + Rm[3] * ray[1] + Rm[6] * ray[2], lvy = Rm[1] * ray[0] + Rm[4] * ray[1] + Rm[7] * ray[2],
+                        lvz = Rm[2] * ray[0] + Rm[5] * ray[1] + Rm[8] * ray[2];
+            if (ray_box(C.site_size[site][0], C.site_size[site][1], C.site_size[site][2], lpx, lpy, lpz, lvx, lvy, lvz) >= 0.0f) contrib = nf;
           }
-          sens[s] = warp_sum(contrib);
+          contrib = warp_sum(contrib);
+          if (lane == 0) S.sens[s] = contrib;
         }
-        if (DBG && A.dbg.sensordata && lane < C.nsensor) {
-          float sv = 0.0f;
-#pragma unroll
-          for (int s = 0; s < MJXB_MAXSENSOR; s++) if (s == lane) sv = sens[s];
-          A.dbg.sensordata[(size_t)env * C.nsensor + lane] = sv;
-        }
+        __syncwarp();
+        if (DBG && A.dbg.sensordata && lane < C.nsensor) A.dbg.sensordata[(size_t)env * C.nsensor + lane] = S.sens[lane];
       }
 
       const float qacc_solver = qacc;  // qacc_warmstart <- solver qacc (mjx solver.solve tail)
@@ -1445,7 +1447,8 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
 
       // ---------------------------------------------------------------- integrate (mjx forward._advance)
       if (integrate_pass) {
-        v = v + qacc_int * h;
+        q = S.vec[VQPOS][lane];
+        v = S.vec[VQVEL][lane] + qacc_int * h;
         __syncwarp();
         S.vec[VQVEL][lane] = (lane < NV) ? v : 0.0f;
         __syncwarp();
@@ -1467,6 +1470,9 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
           }
         }
         tm = tm + h;
+      } else {
+        q = S.vec[VQPOS][lane];
+        v = S.vec[VQVEL][lane];
       }
       ws = qacc_solver;
       if (!(fabsf(q) < 3.0e38f) || !(fabsf(v) < 3.0e38f)) status |= MJXB_STATUS_NAN;
@@ -1483,13 +1489,14 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
         const float roll = atan2f(2.0f * (qw * qx + qy * qz), 1.0f - 2.0f * (qx * qx + qy * qy));
         const float pitch = asinf(clampf(2.0f * (qw * qy - qz * qx), -1.0f, 1.0f));
         const float yaw = atan2f(2.0f * (qw * qz + qx * qy), 1.0f - 2.0f * (qy * qy + qz * qz));
-        float sr = 0.0f, sl = 0.0f;
-#pragma unroll
-        for (int s = 0; s < MJXB_MAXSENSOR; s++) { if (s == cfg.touch_sensor_right_id) sr = sens[s]; if (s == cfg.touch_sensor_left_id) sl = sens[s]; }
+        const float sr = S.sens[cfg.touch_sensor_right_id], sl = S.sens[cfg.touch_sensor_left_id];
         const bool rcon = sr > 0.0f, lcon = sl > 0.0f;
         const float new_stance = (rcon && lcon) ? 0.0f : (rcon && !lcon) ? 1.0f : (!rcon && lcon) ? 2.0f : 3.0f;
         float flip, tx, ty, tz, close_count, stance, stance_time, last_pot, ep, dist_obs, dxo, dyo;
         if (mode == MODE_ENV_STEP) {
+          aux = (lane < MJXB_AUX_DIM) ? A.in.aux[(size_t)env * MJXB_AUX_DIM + lane] : 0.0f;  // loaded late: nothing has overwritten it yet
+          float qfrc_act = 0.0f;   // gear * clip(ctrl), recomputed rather than kept alive through the solver
+          if (lane < NV && C.dof_act[lane] >= 0) qfrc_act = C.dof_gear[lane] * clampf(S.vec[VCTRL][C.dof_act[lane]], C.dof_ctrl_lo[lane], C.dof_ctrl_hi[lane]);
           flip = __shfl_sync(FULL, aux, 0); tx = __shfl_sync(FULL, aux, 1); ty = __shfl_sync(FULL, aux, 2); tz = __shfl_sync(FULL, aux, 3);
           close_count = __shfl_sync(FULL, aux, 4); stance = __shfl_sync(FULL, aux, 5); stance_time = __shfl_sync(FULL, aux, 6);
           last_pot = __shfl_sync(FULL, aux, 7); ep = __shfl_sync(FULL, aux, 8);
