@@ -330,7 +330,10 @@ int launch(const mjxb_model* mc, const StepArgs& args_in, bool dbg, cudaStream_t
     else if (ls) mjxb_step_kernel<false, CAPv, CCv, Wv, true><<<G, B, SM, stream>>>(m->dev, m->dev_pp, args);                   \
     else mjxb_step_kernel<false, CAPv, CCv, Wv, false><<<G, B, SM, stream>>>(m->dev, m->dev_pp, args);                          \
   } while (0)
-  MJXB_LAUNCH(CAP_MAIN, MAXCC_MAIN, WARPS_MAIN, grid, warps * 32, smem_main);
+  // hot instantiation: one step per launch, Newton + exact line search, resets deferred (or none requested)
+  const bool single = !dbg && ls && args.nsteps == 1 && (!(args.mode == MODE_ENV_STEP && args.autoreset) || args.reset_list != nullptr);
+  if (single) mjxb_step_kernel<false, CAP_MAIN, MAXCC_MAIN, WARPS_MAIN, true, true><<<grid, warps * 32, smem_main, stream>>>(m->dev, m->dev_pp, args);
+  else MJXB_LAUNCH(CAP_MAIN, MAXCC_MAIN, WARPS_MAIN, grid, warps * 32, smem_main);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) {  // mid tier (64 rows / 24 contacts) over the envs the main tile could not hold; usually few: exits at once when empty
     args.in_count = ovf; args.in_done = ovf + 1; args.in_list = listA; args.out_count = ovf + 2; args.out_list = listB;
@@ -426,6 +429,7 @@ int mjxb_model_create(const void* blob, size_t blob_bytes, const mjxb_env_config
   CUX(cudaFuncSetAttribute(mjxb_step_kernel<DBGv, CAP_MID, MAXCC_MID, WARPS_MID, LSv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_mid)); \
   CUX(cudaFuncSetAttribute(mjxb_step_kernel<DBGv, CAP_BIG, MAXCC_BIG, WARPS_BIG, LSv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_big));
   MJXB_SMEM_ATTR(false, true) MJXB_SMEM_ATTR(true, true) MJXB_SMEM_ATTR(false, false) MJXB_SMEM_ATTR(true, false)
+  CUX(cudaFuncSetAttribute(mjxb_step_kernel<false, CAP_MAIN, MAXCC_MAIN, WARPS_MAIN, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem));
 #undef MJXB_SMEM_ATTR
   CUX(cudaMalloc(&m->dev, sizeof(DevModel)));
   CUX(cudaMalloc(&m->dev_pp, sizeof(pp)));

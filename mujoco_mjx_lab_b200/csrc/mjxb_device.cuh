@@ -436,7 +436,8 @@ __device__ __forceinline__ void group_sync(int warp, int g) {
 }
 
 // ------------------------------------------------------------------------------------------- the kernel
-template <bool DBG, int CAP, int MAXCC, int MAXW, bool LS_EXACT>
+// SINGLE: one step per launch and resets always deferred -> no loop-carried per-env registers across the step / pass loops.
+template <bool DBG, int CAP, int MAXCC, int MAXW, bool LS_EXACT, bool SINGLE = false>
 __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel* __restrict__ gmodel, const PairParam* __restrict__ pair_param,
                                                             StepArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -517,13 +518,14 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
     float tgt_x = 0.0f, tgt_y = 0.0f, tgt_z = 0.0f, flip_r = 0.0f, vmag_r = 0.0f;
     int did_reset = 0;
 
-    for (int istep = 0; istep < A.nsteps; istep++) {
+    const int nsteps = SINGLE ? 1 : A.nsteps;
+    for (int istep = 0; istep < nsteps; istep++) {
       if (mode == MODE_SPEED_TEST) {  // mjx_humanoid_speed_test.py:50-53: make_data, qvel[0] = vel
         q = lane < C.nq ? C.qpos0[lane] : 0.0f;
         v = (lane == 0) ? A.vel[env] : 0.0f;
         ws = 0.0f; ctrl = 0.0f; tm = 0.0f;
       }
-      for (int pass = 0; pass < 2; pass++) {  // pass 1 only for the fused auto-reset (no CTA barriers there)
+      for (int pass = 0; pass < (SINGLE ? 1 : 2); pass++) {  // pass 1 only for the inline auto-reset (no CTA barriers there)
       if (mode == MODE_ENV_RESET) {
         // ------------------------------------------------------------ single_reset state init (src/envs.py:117-131,147)
         const uint32_t key0 = A.keys[2 * (size_t)env], key1 = A.keys[2 * (size_t)env + 1];
@@ -1549,7 +1551,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
         const bool done_env = (mode == MODE_ENV_STEP) && (fmaxf(out_term, out_trunc) > 0.0f);
         if (done_env && A.autoreset) {  // train_ppo.py:150-161 fused
           did_reset = 1;
-          if (defer) {
+          if (defer || SINGLE) {
             deferred = true;             // queued below; the reset phase of this launch re-initialises it
           } else {
             mode = MODE_ENV_RESET;       // inline: re-run the pipeline in reset mode for this env
