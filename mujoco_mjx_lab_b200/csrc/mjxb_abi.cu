@@ -335,6 +335,8 @@ int launch(const mjxb_model* mc, const StepArgs& args_in, bool dbg, cudaStream_t
   if (single) mjxb_step_kernel<false, CAP_MAIN, MAXCC_MAIN, WARPS_MAIN, true, true><<<grid, warps * 32, smem_main, stream>>>(m->dev, m->dev_pp, args);
   else MJXB_LAUNCH(CAP_MAIN, MAXCC_MAIN, WARPS_MAIN, grid, warps * 32, smem_main);
   cudaError_t e = cudaGetLastError();
+  const bool sync_tiers = getenv("MJXB_SYNC_TIERS") != nullptr;  // debugging aid: attribute a device fault to its tier
+  if (sync_tiers && e == cudaSuccess) { e = cudaStreamSynchronize(stream); if (e != cudaSuccess) fprintf(stderr, "[mjxb] main tier failed: %s\n", cudaGetErrorString(e)); }
   if (e == cudaSuccess) {  // mid tier (64 rows / 24 contacts) over the envs the main tile could not hold; usually few: exits at once when empty
     args.in_count = ovf; args.in_done = ovf + 1; args.in_list = listA; args.out_count = ovf + 2; args.out_list = listB;
     const int wm = m->warps_mid;
@@ -343,6 +345,7 @@ int launch(const mjxb_model* mc, const StepArgs& args_in, bool dbg, cudaStream_t
     args.reset_stride = ((args.n_env + gridm * wm - 1) / (gridm * wm)) * wm;
     MJXB_LAUNCH(CAP_MID, MAXCC_MID, WARPS_MID, gridm, wm * 32, m->smem_mid);
     e = cudaGetLastError();
+    if (sync_tiers && e == cudaSuccess) { e = cudaStreamSynchronize(stream); if (e != cudaSuccess) fprintf(stderr, "[mjxb] mid tier failed: %s\n", cudaGetErrorString(e)); }
   }
   if (e == cudaSuccess) {  // big tier: holds every static row / contact slot of the model
     args.in_count = ovf + 2; args.in_done = ovf + 3; args.in_list = listB; args.out_count = nullptr; args.out_list = nullptr;
@@ -353,6 +356,7 @@ int launch(const mjxb_model* mc, const StepArgs& args_in, bool dbg, cudaStream_t
     MJXB_LAUNCH(CAP_BIG, MAXCC_BIG, WARPS_BIG, gridb, wb * 32, m->smem_big);
 #undef MJXB_LAUNCH
     e = cudaGetLastError();
+    if (sync_tiers && e == cudaSuccess) { e = cudaStreamSynchronize(stream); if (e != cudaSuccess) fprintf(stderr, "[mjxb] big tier failed: %s\n", cudaGetErrorString(e)); }
   }
   if (cur != m->device) cudaSetDevice(cur);
   if (e != cudaSuccess) return cuda_fail(e, "mjxb_step_kernel launch");

@@ -1007,22 +1007,22 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
         r = nrow + __popc(mk & lt_mask);
         if (cand && r < CAP) { S.rinfo[r] = ROW_TENDON | (lane << 2) | (sgn < 0.0f ? 1 << 10 : 0); S.rJaref[r] = pos; }
         nrow += __popc(mk);
-        // contacts: exclusive scan of rows per candidate
-        int nr = 0;
-        if (lane < ncc) nr = ((S.cc_pair[lane] >> 20) > 1) ? 4 : 1;
-        int scan = nr;
+        // contacts: exclusive scan of rows per candidate, 32 candidates per strip (the big tier holds up to 176)
+        int total = 0;
+        for (int cb = 0; cb < ncc; cb += 32) {
+          const int c = cb + lane;
+          int nr = 0;
+          if (c < ncc) nr = ((S.cc_pair[c] >> 20) > 1) ? 4 : 1;
+          int scan = nr;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          int t = __shfl_up_sync(FULL, scan, o);
-          if (lane >= o) scan += t;
+          for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(FULL, scan, o);
+            if (lane >= o) scan += t;
+          }
+          const int rbase = nrow + total + scan - nr;
+          if (c < ncc) S.cc_row[c] = (rbase + nr <= CAP) ? rbase : -1;
+          total += __shfl_sync(FULL, scan, 31);
         }
-        int rbase = nrow + scan - nr;
-        bool fits = (lane < ncc) && (rbase + nr <= CAP);
-        unsigned fm = __ballot_sync(FULL, fits);
-        int nfit = __popc(fm);  // candidates are dropped from the tail
-        if (lane < ncc) S.cc_row[lane] = fits ? rbase : -1;
-        int total = __shfl_sync(FULL, scan, 31);
-        (void)nfit;
         if (nrow + total > CAP) overflow = true;
         if (overflow) { total = 0; ncc = 0; nrow = min(nrow, CAP); }  // results are discarded; keep the row set inside the tile
         const int nrow_lim = nrow;
@@ -1411,31 +1411,29 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
 
       // ---------------------------------------------------------------- touch sensors (mjx sensor.sensor_acc / engine_sensor.c mjSENS_TOUCH)
       {
-        float nf = 0.0f;
-        int b1 = -1, b2 = -1;
-        if (lane < ncc) {
-          const int pr = S.cc_pair[lane], p = pr & 0xffff, rb = S.cc_row[lane];
-          const uint32_t w0 = C.pair_w0[p];
-          b1 = C.geom_body[w0 & 0xff]; b2 = C.geom_body[(w0 >> 8) & 0xff];
-          nf = S.rforce[rb];
-          if ((pr >> 20) > 1) nf = ((S.rforce[rb] + S.rforce[rb + 1]) + S.rforce[rb + 2]) + S.rforce[rb + 3];
-        }
 #pragma unroll 1
         for (int s = 0; s < C.nsensor; s++) {
           float contrib = 0.0f;
           const int site = C.sensor_site[s], sb = C.site_body[site];
-          if (lane < ncc && nf > 0.0f && (sb == b1 || sb == b2)) {
-            float ray[3] = {S.cc_n[lane][0] * nf, S.cc_n[lane][1] * nf, S.cc_n[lane][2] * nf};
+          for (int c = lane; c < ncc; c += 32) {
+            const int pr = S.cc_pair[c], p = pr & 0xffff, rb = S.cc_row[c];
+            const uint32_t w0 = C.pair_w0[p];
+            const int b1 = C.geom_body[w0 & 0xff], b2 = C.geom_body[(w0 >> 8) & 0xff];
+            if (sb != b1 && sb != b2) continue;
+            float nf = S.rforce[rb];
+            if ((pr >> 20) > 1) nf = ((S.rforce[rb] + S.rforce[rb + 1]) + S.rforce[rb + 2]) + S.rforce[rb + 3];
+            if (!(nf > 0.0f)) continue;
+            float ray[3] = {S.cc_n[c][0] * nf, S.cc_n[c][1] * nf, S.cc_n[c][2] * nf};
             normalize3(ray);
             if (sb == b2) { ray[0] = -ray[0]; ray[1] = -ray[1]; ray[2] = -ray[2]; }
-            const float dx = S.cc_pos[lane][0] - S.site_xpos[site][0], dy = S.cc_pos[lane][1] - S.site_xpos[site][1],
-                        dz = S.cc_pos[lane][2] - S.site_xpos[site][2];
+            const float dx = S.cc_pos[c][0] - S.site_xpos[site][0], dy = S.cc_pos[c][1] - S.site_xpos[site][1],
+                        dz = S.cc_pos[c][2] - S.site_xpos[site][2];
             const float* Rm = S.site_xmat[site];
             const float lpx = Rm[0] * dx + Rm[3] * dy + Rm[6] * dz, lpy = Rm[1] * dx + Rm[4] * dy + Rm[7] * dz,
                         lpz = Rm[2] * dx + Rm[5] * dy + Rm[8] * dz;
             const float lvx = Rm[0] * ray[0] + Rm[3] * ray[1] + Rm[6] * ray[2], lvy = Rm[1] * ray[0] + Rm[4] * ray[1] + Rm[7] * ray[2],
                         lvz = Rm[2] * ray[0] + Rm[5] * ray[1] + Rm[8] * ray[2];
-            if (ray_box(C.site_size[site][0], C.site_size[site][1], C.site_size[site][2], lpx, lpy, lpz, lvx, lvy, lvz) >= 0.0f) contrib = nf;
+            if (ray_box(C.site_size[site][0], C.site_size[site][1], C.site_size[site][2], lpx, lpy, lpz, lvx, lvy, lvz) >= 0.0f) contrib += nf;
           }
           contrib = warp_sum(contrib);
           if (lane == 0) S.sens[s] = contrib;

@@ -69,6 +69,11 @@ def make_states(model, n, seed, kind):
         q[:, 3:7] = rand_quat(rng, n, 0.25)
         q[:, 2] -= rng.uniform(0.0, 0.08, n)
         v = rng.normal(size=(n, nv)) * 0.5
+    elif kind == "crumple":      # folded far beyond the joint limits and sunk into the floor: > 32 candidate contacts, ~100 rows
+        q[:, 7:] = rng.uniform(-3.14, 3.14, (n, nq - 7))
+        q[:, 2] = rng.uniform(-0.6, -0.2, n)
+        q[:, 3:7] = rand_quat(rng, n, 3.0)
+        v = rng.normal(size=(n, nv))
     else:
         raise ValueError(kind)
     warm = rng.normal(size=(n, nv)) * (0.0 if kind == "free" else 5.0)

@@ -33,3 +33,30 @@ def test_overflow_envs_match_oracle(model, oracle):
     # and a second launch (counters were reset by the consuming pass) gives identical bits
     _, out2 = mjx.forward(sysm, mjx.Data(t(q), t(v), t(w), torch.zeros(n, device="cuda"), t(c)), debug=True)
     assert torch.equal(out["qacc"], out2["qacc"])
+
+
+def test_more_than_32_candidate_contacts(model, oracle):
+    """Crumpled, sunk poses: up to ~46 candidate contacts and > 100 rows per env -- the big tier's strip loops over contacts
+    (row assignment, touch sensors); candidate set bit-exact, qacc and sensors f32-equivalent."""
+    sysm = mjx.put_model(model)
+    n = 256
+    q, v, w, c = helpers.make_states(model, n, 1, "crumple")
+    ref = oracle.forward(q, v, w, c, prec="f64", debug=True)
+    r32 = oracle.forward(q, v, w, c, prec="f32", debug=True)
+    ncon = (ref["con_dist"] < 0).sum(axis=1)
+    many = ncon > 32
+    assert many.sum() >= 3, "seed no longer produces envs with more than 32 candidate contacts"
+    t = lambda a: torch.tensor(a, dtype=torch.float32, device="cuda")
+    _, out = mjx.forward(sysm, mjx.Data(t(q), t(v), t(w), torch.zeros(n, device="cuda"), t(c)), debug=True)
+    torch.cuda.synchronize()
+    status = out["status"].cpu().numpy()
+    assert ((status & 2) != 0)[many].all() and ((status & 1) == 0).all()
+    near = np.abs(ref["con_dist"]) < 1e-5                          # sign of a ~0 distance may differ in f32
+    assert ((((out["con_dist"].cpu().numpy() < 0) != (ref["con_dist"] < 0)) & ~near).sum(axis=1) == 0).all()
+    from test_gpu_parity import assert_f32_equivalent
+    rel = lambda a, b: np.abs(a - b) / np.maximum(1, np.abs(b))
+    g = out["qacc"].double().cpu().numpy()
+    assert_f32_equivalent(rel(g, ref["qacc"]).max(axis=1), rel(r32["qacc"], ref["qacc"]).max(axis=1), 1e-4, "qacc of crumpled envs")
+    s = out["sensordata"].double().cpu().numpy()
+    assert_f32_equivalent(rel(s, ref["sensordata"]).max(axis=1), rel(r32["sensordata"], ref["sensordata"]).max(axis=1), 1e-4,
+                          "touch sensors of crumpled envs")
