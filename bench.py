@@ -181,11 +181,10 @@ def main():
     # ---- end to end through the host-buffer ABI call (pinned host buffers; H2D + kernel + D2H timed)
     L, h = _lib.lib(), env_sys.handle
     pin = lambda *s, dt=torch.float32: torch.empty(*s, dtype=dt, pin_memory=True)
-    h_act = [pin(n, nu) for _ in range(2)]
-    for b in h_act:
-        b.copy_(acts[0].cpu())
-    h_keys = pin(n, 2, dt=torch.int32)
-    h_keys.copy_(keys[0].cpu())
+    h_act = [pin(n, nu) for _ in range(nbuf)]                        # the same action / key sequence as the device-resident leg
+    h_keys = [pin(n, 2, dt=torch.int32) for _ in range(nbuf)]
+    for b, src in zip(h_act + h_keys, acts + keys):
+        b.copy_(src.cpu())
     h_obs, h_r, h_te, h_tr = pin(n, env_sys.obs_dim), pin(n), pin(n), pin(n)
     d, aux = state
     host_state = [np.ascontiguousarray(t.detach().cpu().numpy()) for t in (d.qpos, d.qvel, d.qacc_warmstart, d.time, aux)]  # keep alive
@@ -193,7 +192,7 @@ def main():
     e2e_steps = max(3, min(args.steps, 20))
 
     def e2e_step(i):
-        _lib.check(L.mjxb_step_autoreset_host(h, n, h_act[i % 2].data_ptr(), h_keys.data_ptr(), h_obs.data_ptr(), h_r.data_ptr(),
+        _lib.check(L.mjxb_step_autoreset_host(h, n, h_act[i % nbuf].data_ptr(), h_keys[i % nbuf].data_ptr(), h_obs.data_ptr(), h_r.data_ptr(),
                                               h_te.data_ptr(), h_tr.data_ptr()), "step_autoreset_host")
     for i in range(3):
         e2e_step(i)

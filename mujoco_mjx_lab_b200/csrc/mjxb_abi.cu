@@ -38,6 +38,12 @@ struct Arena {  // device-resident env batch for the *_host entry points
   cudaStream_t pipe[kSlots] = {nullptr, nullptr, nullptr};
   int* pipe_ovf[kSlots] = {nullptr, nullptr, nullptr};
   int chunk = 0;
+  // direct pipeline (pinned caller buffers): one launch; inputs stream in behind per-chunk ready flags, obs go straight to the host
+  static constexpr int kReadyMax = 64;
+  unsigned* ready = nullptr;      // device flags [kReadyMax]
+  unsigned* ready_src = nullptr;  // pinned source of the flag copies
+  unsigned epoch = 0;
+  int ready_shift = 0;
 };
 
 }  // namespace
@@ -60,6 +66,9 @@ void arena_free(Arena& a) {
   for (float** p : ps) { if (*p) cudaFree(*p); *p = nullptr; }
   if (a.keys) cudaFree(a.keys);
   a.keys = nullptr;
+  if (a.ready) cudaFree(a.ready);
+  if (a.ready_src) cudaFreeHost(a.ready_src);
+  a.ready = nullptr; a.ready_src = nullptr;
   if (a.stream) cudaStreamDestroy(a.stream);
   a.stream = nullptr;
   for (int i = 0; i < Arena::kSlots; i++) {
@@ -97,6 +106,12 @@ int arena_ensure(mjxb_model* m, int n) {
     CU(cudaMalloc(&a.pipe_ovf[i], (3 * (size_t)a.chunk + 4 + kResetPad) * sizeof(int)));
     CU(cudaMemsetAsync(a.pipe_ovf[i], 0, 4 * sizeof(int), a.stream));
   }
+  CU(cudaMalloc(&a.ready, Arena::kReadyMax * sizeof(unsigned)));
+  CU(cudaMemsetAsync(a.ready, 0, Arena::kReadyMax * sizeof(unsigned), a.stream));
+  CU(cudaHostAlloc(&a.ready_src, Arena::kReadyMax * sizeof(unsigned), cudaHostAllocDefault));
+  a.epoch = 0;
+  a.ready_shift = 12;  // input chunks of 2^shift envs: about 8 per step, never more than kReadyMax
+  while (((n + (1 << a.ready_shift) - 1) >> a.ready_shift) > 8) a.ready_shift++;
   CU(cudaStreamSynchronize(a.stream));
   a.n = n;
   return MJXB_OK;
@@ -312,7 +327,9 @@ int launch(const mjxb_model* mc, const StepArgs& args_in, bool dbg, cudaStream_t
   int* listB = ovf + 4 + cap;
   args.in_count = nullptr; args.in_list = nullptr; args.in_done = nullptr; args.out_count = ovf; args.out_list = listA;
   args.reset_list = (getenv("MJXB_INLINE_RESET") != nullptr) ? nullptr : ovf + 4 + 2 * (size_t)cap;
-  { const char* e = getenv("MJXB_LOCKSTEP"); args.lockstep = e ? atoi(e) : 1; }  // default on; MJXB_LOCKSTEP=0 disables (profiling aid)
+  // 3 (default): CTA barriers at the round top, the solver entry and every factor/solve round; 1: round top + solver entry/exit only;
+  // 0: none (profiling aid)
+  { const char* e = getenv("MJXB_LOCKSTEP"); args.lockstep = e ? atoi(e) : 3; }
   { const char* e = getenv("MJXB_LOCKSTEP_GROUP"); args.lockstep_group = e ? atoi(e) : 0; }
   // small batches: spread the envs over every SM (fewer warps per CTA run faster than 16 sharing one SM's issue slots)
   int warps = m->warps;
@@ -337,6 +354,7 @@ int launch(const mjxb_model* mc, const StepArgs& args_in, bool dbg, cudaStream_t
   cudaError_t e = cudaGetLastError();
   const bool sync_tiers = getenv("MJXB_SYNC_TIERS") != nullptr;  // debugging aid: attribute a device fault to its tier
   if (sync_tiers && e == cudaSuccess) { e = cudaStreamSynchronize(stream); if (e != cudaSuccess) fprintf(stderr, "[mjxb] main tier failed: %s\n", cudaGetErrorString(e)); }
+  args.in_ready = nullptr;  // only the first pass waits for streamed inputs
   if (e == cudaSuccess) {  // mid tier (64 rows / 24 contacts) over the envs the main tile could not hold; usually few: exits at once when empty
     args.in_count = ovf; args.in_done = ovf + 1; args.in_list = listA; args.out_count = ovf + 2; args.out_list = listB;
     const int wm = m->warps_mid;
@@ -550,6 +568,15 @@ int mjxb_reset_host(mjxb_model* m, int32_t n_env, const uint32_t* keys_host, flo
   return MJXB_OK;
 }
 
+// device-visible alias of a pinned / registered host pointer (UVA); false for pageable memory
+static bool host_dev_ptr(const void* p, void** dp) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  if (at.type != cudaMemoryTypeHost || at.devicePointer == nullptr) return false;
+  *dp = at.devicePointer;
+  return true;
+}
+
 static int step_host_impl(mjxb_model* m, int32_t n_env, const float* action_host, const uint32_t* keys_host, float* obs_host,
                           float* reward_host, float* terminated_host, float* truncated_host) {
   if (!m || n_env <= 0 || !action_host || !obs_host || !reward_host || !terminated_host || !truncated_host) return MJXB_EINVAL;
@@ -557,6 +584,46 @@ static int step_host_impl(mjxb_model* m, int32_t n_env, const float* action_host
   if (a.n != n_env) return MJXB_EINVAL;  // reset_host / state_set_host must have created the batch
   const int nu = m->host.nu, od = m->host.cfg.obs_dim, nq = m->host.nq, nv = m->host.nv;
   CU(cudaStreamSynchronize(a.stream));  // state_set_host / reset_host ran on a.stream
+  // Direct pipeline when the caller's buffers are pinned (device-visible): ONE launch over the whole batch; action / keys stream in
+  // on the copy stream in ~8 chunks, each followed by a 4-byte flag copy the kernel waits on (copy engines only: a flag *kernel* could
+  // never be scheduled beside the persistent grid); obs are stored by the kernel straight into the caller's mapped buffer.
+  void *obs_dev = nullptr, *tmp = nullptr;
+  const bool direct = getenv("MJXB_HOST_DIRECT") ? atoi(getenv("MJXB_HOST_DIRECT")) != 0 : true;
+  if (direct && host_dev_ptr(obs_host, &obs_dev) && host_dev_ptr(action_host, &tmp) && (!keys_host || host_dev_ptr(keys_host, &tmp))) {
+    cudaStream_t main_st = a.pipe[0], copy_st = a.pipe[1];
+    a.epoch++;
+    const int csz = 1 << a.ready_shift, nchunk = (n_env + csz - 1) / csz;
+    for (int k = 0; k < nchunk; k++) {
+      const size_t o = (size_t)k * csz, c = (size_t)((n_env - k * csz < csz) ? n_env - k * csz : csz);
+      a.ready_src[k] = a.epoch;
+      CU(cudaMemcpyAsync(a.action + o * nu, action_host + o * nu, c * nu * 4, cudaMemcpyHostToDevice, copy_st));
+      if (keys_host) CU(cudaMemcpyAsync(a.keys + o * 2, keys_host + o * 2, c * 8, cudaMemcpyHostToDevice, copy_st));
+      CU(cudaMemcpyAsync(a.ready + k, a.ready_src + k, sizeof(unsigned), cudaMemcpyHostToDevice, copy_st));
+    }
+    StepArgs sa;
+    memset(&sa, 0, sizeof(sa));
+    sa.n_env = n_env; sa.mode = MODE_ENV_STEP; sa.nsteps = 1; sa.autoreset = keys_host ? 1 : 0; sa.in = arena_state(a); sa.out = sa.in;
+    sa.action = a.action; sa.keys = keys_host ? a.keys : nullptr; sa.obs = static_cast<float*>(obs_dev); sa.reward = a.reward;
+    sa.terminated = a.term; sa.truncated = a.trunc;
+    sa.in_ready = a.ready; sa.in_ready_shift = a.ready_shift; sa.in_ready_epoch = a.epoch;
+    const bool obs_direct = getenv("MJXB_DIRECT_OBS") ? atoi(getenv("MJXB_DIRECT_OBS")) != 0 : true;
+    const bool sc_direct = getenv("MJXB_DIRECT_SCALARS") ? atoi(getenv("MJXB_DIRECT_SCALARS")) != 0 : true;
+    void *rd = nullptr, *td = nullptr, *ud = nullptr;
+    const bool scd = sc_direct && host_dev_ptr(reward_host, &rd) && host_dev_ptr(terminated_host, &td) && host_dev_ptr(truncated_host, &ud);
+    if (!obs_direct) sa.obs = a.obs;
+    if (scd) { sa.reward = (float*)rd; sa.terminated = (float*)td; sa.truncated = (float*)ud; }
+    int rc = launch(m, sa, false, main_st);
+    if (rc) { cudaStreamSynchronize(copy_st); return rc; }
+    if (!obs_direct) CU(cudaMemcpyAsync(obs_host, a.obs, (size_t)n_env * od * 4, cudaMemcpyDeviceToHost, main_st));
+    if (!scd) {
+    CU(cudaMemcpyAsync(reward_host, a.reward, (size_t)n_env * 4, cudaMemcpyDeviceToHost, main_st));
+    CU(cudaMemcpyAsync(terminated_host, a.term, (size_t)n_env * 4, cudaMemcpyDeviceToHost, main_st));
+    CU(cudaMemcpyAsync(truncated_host, a.trunc, (size_t)n_env * 4, cudaMemcpyDeviceToHost, main_st));
+    }
+    CU(cudaStreamSynchronize(copy_st));
+    CU(cudaStreamSynchronize(main_st));
+    return MJXB_OK;
+  }
   int slot = 0;
   for (int lo = 0; lo < n_env; lo += a.chunk, slot = (slot + 1) % Arena::kSlots) {
     const int cn = (n_env - lo < a.chunk) ? n_env - lo : a.chunk;

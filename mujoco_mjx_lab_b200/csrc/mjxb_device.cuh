@@ -97,6 +97,9 @@ struct StepArgs {
   int* reset_list; int reset_stride;
   int lockstep;          // CTA barriers keep the warps of an SM in the same code region (instruction-cache locality)
   int lockstep_group;    // warps per barrier group (0 = the whole CTA)
+  // host-buffer pipeline: action / keys arrive in chunks of (1 << in_ready_shift) envs while the kernel already runs; the copy
+  // stream writes in_ready_epoch into in_ready[chunk] after each chunk (NULL: every input is resident at launch)
+  const unsigned* in_ready; int in_ready_shift; unsigned in_ready_epoch;
   mjxb_debug dbg;
 };
 
@@ -423,6 +426,9 @@ __device__ __forceinline__ float chol_solve_rows(WS& S, int lane, const float (&
 struct LSPoint { float alpha, cost, d0, d1; };
 
 }  // namespace mjxb
+#ifndef MJXB_FACTOR_REUSE
+#define MJXB_FACTOR_REUSE 1
+#endif
 #include "mjxb_chol_tree.cuh"
 namespace mjxb {
 
@@ -495,13 +501,26 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
     // 230 KB of shared memory cannot hold spills): they are published to shared memory here and re-read where they are used.
     float q = 0.0f, v = 0.0f, ws = 0.0f, ctrl = 0.0f, tm = 0.0f, aux = 0.0f;
     int status = consuming ? MJXB_STATUS_ROW_SPILL : 0;
+    if (A.in_ready != nullptr && !reset_phase) {  // wait for this env's chunk of action / keys (copy engine -> flag, L2-coherent)
+      if (lane == 0) {
+        const unsigned* flag = A.in_ready + (env >> A.in_ready_shift);
+#pragma unroll 1
+        for (int spin = 0; spin < (1 << 22); spin++) {  // bounded (~2 s): a lost copy must not hang the device
+          unsigned seen;
+          asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+          if ((int)(seen - A.in_ready_epoch) >= 0) break;
+          __nanosleep(500);
+        }
+      }
+      __syncwarp();
+    }
     {
       float action = 0.0f;
       if (mode == MODE_ENV_STEP || mode == MODE_PHYS_STEP || mode == MODE_FORWARD) {
         if (lane < C.nq) q = A.in.qpos[(size_t)env * C.nq + lane];
         if (lane < NV) { v = A.in.qvel[(size_t)env * NV + lane]; ws = A.in.qacc_warmstart[(size_t)env * NV + lane]; }
         tm = A.in.time[env];
-        if (A.action != nullptr && lane < C.nu) action = A.action[(size_t)env * C.nu + lane];
+        if (A.action != nullptr && lane < C.nu) action = __ldcg(A.action + (size_t)env * C.nu + lane);
       }
       if (mode == MODE_ENV_STEP) {
         const float flip = A.in.aux[(size_t)env * MJXB_AUX_DIM];
@@ -528,7 +547,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
       for (int pass = 0; pass < (SINGLE ? 1 : 2); pass++) {  // pass 1 only for the inline auto-reset (no CTA barriers there)
       if (mode == MODE_ENV_RESET) {
         // ------------------------------------------------------------ single_reset state init (src/envs.py:117-131,147)
-        const uint32_t key0 = A.keys[2 * (size_t)env], key1 = A.keys[2 * (size_t)env + 1];
+        const uint32_t key0 = __ldcg(A.keys + 2 * (size_t)env), key1 = __ldcg(A.keys + 2 * (size_t)env + 1);
         uint32_t k1a, k1b, k2a, k2b, k3a, k3b, k4a, k4b;
         threefry2x32(key0, key1, 0u, 0u, k1a, k1b);
         threefry2x32(key0, key1, 0u, 1u, k2a, k2b);
@@ -1136,6 +1155,9 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
       float qas = 0.0f, qacc = 0.0f, Ma = 0.0f, qfc = 0.0f, grad = 0.0f, search = 0.0f;
       float gauss = 0.0f, cost = 0.0f, prev_cost = 0.0f, prev_grad = 0.0f, prev_Mgrad = 0.0f;
       int niter = 0, phase = 0;
+      bool factor_valid = false;           // S.L / dinv_keep hold the factor of H for the current active set (tree pattern only)
+      float* dinv_keep = &S.gpos[0][0];    // geom frames are dead after the collision stage: 32 floats of 1/R_ii
+      static_assert(sizeof(S.gpos) >= 32 * sizeof(float), "dinv_keep needs 32 floats");
       const float scale = 1.0f / (C.meaninertia * (float)max(1, C.nv));
       float qacc_int = 0.0f;
       const bool integrate_pass = (mode == MODE_ENV_STEP || mode == MODE_PHYS_STEP || mode == MODE_SPEED_TEST);
@@ -1157,6 +1179,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
       };
 
       while (true) {
+        if (A.lockstep == 3 && pass == 0) __syncthreads_or(1);  // re-align the warps of the CTA at every factor/solve round (finished warps answer below)
         asm volatile("" : "+r"(phase));  // keep `phase` opaque: the compiler otherwise clones the whole factor/solve body per phase
         if (phase == 1) {  // mjx solver.solve cond(): evaluated before paying for the next factorisation
           bool done;
@@ -1174,45 +1197,53 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
             phase = 2;
           }
         }
-        // ---- assemble the rows of the system matrix in registers
-        float a[NVP];
-        {
-          const float4* row = reinterpret_cast<const float4*>(&S.M[(lane < NV ? lane : 0) * NVP]);
-#pragma unroll
-          for (int g = 0; g < NVP / 4; g++) {
-            float4 m = row[g];
-            a[4 * g] = m.x; a[4 * g + 1] = m.y; a[4 * g + 2] = m.z; a[4 * g + 3] = m.w;
-          }
-        }
-        if (phase == 2) {
-          const float hd = (lane < NV) ? h * C.dof_damping[lane] : 0.0f;
-#pragma unroll
-          for (int j = 0; j < NV; j++) a[j] += (j == lane) ? hd : 0.0f;
-        }
-        if (phase == 1 && (LS_EXACT || C.solver == 2)) {  // Newton: H = M + J^T diag(D*active) J ; CG preconditions with M alone
-          for (int r = 0; r < nrow; r++) {
-            if (!(S.rJaref[r] < 0.0f)) continue;  // row inactive at the current iterate (warp-uniform)
-            const float w = S.rD[r] * S.J[r * NVP + (lane < NVP ? lane : 0)];
-            const float4* jr = reinterpret_cast<const float4*>(&S.J[r * NVP]);
+        // ---- assemble the rows of the system matrix in registers, factor, solve
+        // Newton iterations whose active set did not change since the last factorisation (typically the final, polishing ones)
+        // reuse that factor: H = M + J^T diag(D*active) J would be rebuilt bit for bit, so the solve reads the rows of R kept in S.L.
+        const float rhs = (phase == 0) ? qfs : (phase == 1) ? grad : (qfs + qfc);
+        float x;
+        if (MJXB_FACTOR_REUSE && LS_EXACT && phase == 1 && factor_valid) {
+          x = chol_tree_solve_lds(S, lane, dinv_keep[lane], rhs);
+        } else {
+          float a[NVP];
+          {
+            const float4* row = reinterpret_cast<const float4*>(&S.M[(lane < NV ? lane : 0) * NVP]);
 #pragma unroll
             for (int g = 0; g < NVP / 4; g++) {
-              float4 jj = jr[g];
-              a[4 * g] += w * jj.x; a[4 * g + 1] += w * jj.y; a[4 * g + 2] += w * jj.z; a[4 * g + 3] += w * jj.w;
+              float4 m = row[g];
+              a[4 * g] = m.x; a[4 * g + 1] = m.y; a[4 * g + 2] = m.z; a[4 * g + 3] = m.w;
             }
           }
-        }
-        if (lane >= NV) {  // idle lanes: identity rows keep the arithmetic finite
+          if (phase == 2) {
+            const float hd = (lane < NV) ? h * C.dof_damping[lane] : 0.0f;
 #pragma unroll
-          for (int j = 0; j < NVP; j++) a[j] = 0.0f;
-        }
-        const float rhs = (phase == 0) ? qfs : (phase == 1) ? grad : (qfs + qfc);
-        float dinv, x;
-        if (tree_ok || (phase != 1 && C.tree_chol_ok != 0)) {  // M and M + h*damping always follow the tree pattern; H does unless a row couples two limbs
-          chol_tree(S, lane, a, dinv);
-          x = chol_tree_solve(S, lane, a, dinv, (lane < NV) ? rhs : 0.0f);
-        } else {
-          chol_rows(S, lane, a, dinv);
-          x = chol_solve_rows(S, lane, a, dinv, (lane < NV) ? rhs : 0.0f);
+            for (int j = 0; j < NV; j++) a[j] += (j == lane) ? hd : 0.0f;
+          }
+          if (phase == 1 && (LS_EXACT || C.solver == 2)) {  // Newton: H = M + J^T diag(D*active) J ; CG preconditions with M alone
+            for (int r = 0; r < nrow; r++) {
+              if (!(S.rJaref[r] < 0.0f)) continue;  // row inactive at the current iterate (warp-uniform)
+              const float w = S.rD[r] * S.J[r * NVP + (lane < NVP ? lane : 0)];
+              const float4* jr = reinterpret_cast<const float4*>(&S.J[r * NVP]);
+#pragma unroll
+              for (int g = 0; g < NVP / 4; g++) {
+                float4 jj = jr[g];
+                a[4 * g] += w * jj.x; a[4 * g + 1] += w * jj.y; a[4 * g + 2] += w * jj.z; a[4 * g + 3] += w * jj.w;
+              }
+            }
+          }
+          if (lane >= NV) {  // idle lanes: identity rows keep the arithmetic finite
+#pragma unroll
+            for (int j = 0; j < NVP; j++) a[j] = 0.0f;
+          }
+          float dinv;
+          if (tree_ok || (phase != 1 && C.tree_chol_ok != 0)) {  // M and M + h*damping always follow the tree pattern; H does unless a row couples two limbs
+            chol_tree(S, lane, a, dinv);
+            x = chol_tree_solve(S, lane, a, dinv, (lane < NV) ? rhs : 0.0f);
+            if (MJXB_FACTOR_REUSE && LS_EXACT && phase == 1) { dinv_keep[lane] = dinv; factor_valid = true; }
+          } else {
+            chol_rows(S, lane, a, dinv);
+            x = chol_solve_rows(S, lane, a, dinv, (lane < NV) ? rhs : 0.0f);
+          }
         }
 
         if (phase == 0) {
@@ -1386,7 +1417,13 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
           if (alpha_step != 0.0f) {
             qacc += search * alpha_step;
             Ma += mv * alpha_step;
-            for (int r = lane; r < nrow; r += 32) S.rJaref[r] += S.rjv[r] * alpha_step;
+            bool flip = false;
+            for (int r = lane; r < nrow; r += 32) {
+              const float ja0 = S.rJaref[r], ja1 = ja0 + S.rjv[r] * alpha_step;
+              flip |= (ja0 < 0.0f) != (ja1 < 0.0f);
+              S.rJaref[r] = ja1;
+            }
+            if (LS_EXACT && __any_sync(FULL, flip)) factor_valid = false;
           }
           __syncwarp();
         }
@@ -1395,7 +1432,8 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
         niter++;
       }  // factor/solve loop
 
-      if (A.lockstep > 0 && A.lockstep != 2 && pass == 0) group_sync(warp, A.lockstep_group);  // ... and leave it together (early finishers would idle at the round barrier anyway)
+      if (A.lockstep == 3 && pass == 0) { while (__syncthreads_or(0)) {} }  // finished warps keep answering the per-round barrier
+      else if (A.lockstep > 0 && A.lockstep != 2 && pass == 0) group_sync(warp, A.lockstep_group);  // ... and leave it together (early finishers would idle at the round barrier anyway)
       if (DBG) {
         if (lane < NV) {
           if (A.dbg.qacc) A.dbg.qacc[(size_t)env * NV + lane] = qacc;

@@ -277,6 +277,35 @@ def test_host_buffer_api(model, env):
     assert L.mjxb_step_host(h, n + 1, act.ctypes.data, obs_h.ctypes.data, r_h.ctypes.data, te_h.ctypes.data, tr_h.ctypes.data) == -1
 
 
+def test_host_buffer_api_pinned_direct(model, env):
+    """Pinned caller buffers take the direct pipeline (one launch, inputs behind per-chunk ready flags, obs stored straight into the
+    caller's mapped buffer): same bits as the device-pointer API, over several input chunks and several calls (flag epochs)."""
+    from mujoco_mjx_lab_b200 import _lib
+    v_reset, v_step = env[8], env[9]
+    L, h = _lib.lib(), v_step.sys.handle
+    n = 20000                                                  # 5 input chunks of 4096 envs
+    keys = helpers.ppo_keys(9, n)
+    pin = lambda *shape, dt=torch.float32: torch.zeros(*shape, dtype=dt).pin_memory()
+    obs_h, r_h, te_h, tr_h, act_h = pin(n, 54), pin(n), pin(n), pin(n), pin(n, 21)
+    keys_h = torch.from_numpy(keys.view(np.int32).copy()).pin_memory()
+    _lib.check(L.mjxb_reset_host(h, n, keys_h.data_ptr(), obs_h.data_ptr()))
+    state, obs = v_reset(keys)
+    assert torch.equal(obs_h, obs.cpu())
+    rng = np.random.default_rng(3)
+    for it in range(4):
+        act_h.copy_(torch.from_numpy(np.clip(rng.normal(size=(n, 21)), -1, 1).astype(np.float32)))
+        rk = helpers.ppo_keys(20 + it, n)
+        keys_h.copy_(torch.from_numpy(rk.view(np.int32).copy()))
+        _lib.check(L.mjxb_step_autoreset_host(h, n, act_h.data_ptr(), keys_h.data_ptr(), obs_h.data_ptr(), r_h.data_ptr(),
+                                              te_h.data_ptr(), tr_h.data_ptr()))
+        state, obs, r, te, tr = v_step.autoreset(state, act_h.cuda(), rk)
+        assert torch.equal(obs_h, obs.cpu()) and torch.equal(r_h, r.cpu())
+        assert torch.equal(te_h, te.cpu()) and torch.equal(tr_h, tr.cpu())
+    qpos_h = pin(n, 28)
+    _lib.check(L.mjxb_state_get_host(h, n, qpos_h.data_ptr(), None, None, None, None))
+    assert torch.equal(qpos_h, state[0].qpos.cpu())
+
+
 def test_argument_errors(env):
     from mujoco_mjx_lab_b200 import _lib
     v_reset, v_step = env[8], env[9]

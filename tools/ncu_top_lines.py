@@ -1,31 +1,34 @@
-"""Aggregate an `ncu --page source --csv --print-source cuda,sass` dump by CUDA source line (first kernel in the report)."""
+"""Aggregate an `ncu --page source --csv --print-source cuda,sass` dump by CUDA source line (every source file of the report).
+Usage: python tools/ncu_top_lines.py dump.csv [topn] [sort: samples|inst|smem]"""
 import csv
+import os
 import sys
 
-path, topn = sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 40
+path = sys.argv[1]
+topn = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+sort = sys.argv[3] if len(sys.argv) > 3 else "samples"
 rows = list(csv.reader(open(path)))
-hdr, data, started = None, [], False
+hdr, fname, agg = None, "?", {}
 for r in rows:
-    if r and r[0] == "Function Name":
-        if started:
-            break
-        started = True
+    if r and r[0] == "File Path":
+        fname = os.path.basename(r[1]).replace("mjxb_", "").replace(".cuh", "")
         continue
     if r and r[0] == "Line No":
         hdr = r
+        ci, cs, cw = hdr.index("Instructions Executed"), hdr.index("# Samples"), hdr.index("L1 Wavefronts Shared")
+        cb = hdr.index("stall_barrier")
         continue
     if hdr is None or len(r) < 10 or r[2] != "-":
         continue
     try:
-        data.append((int(r[0]), r[1], int(r[hdr.index("Instructions Executed")]), int(r[hdr.index("# Samples")]),
-                     int(r[hdr.index("L1 Wavefronts Shared")])))
+        key = (fname, int(r[0]))
+        a = agg.setdefault(key, [r[1], 0, 0, 0, 0])
+        a[1] += int(r[ci]); a[2] += int(r[cs]); a[3] += int(r[cw]); a[4] += int(r[cb])
     except ValueError:
         pass
-agg = {}
-for ln, src, ins, smp, wf in data:
-    a = agg.setdefault(ln, [src, 0, 0, 0])
-    a[1] += ins; a[2] += smp; a[3] += wf
-ti, ts, tw = sum(a[1] for a in agg.values()), sum(a[2] for a in agg.values()), sum(a[3] for a in agg.values())
-print(f"total warp-instructions {ti}  samples {ts}  smem wavefronts {tw}")
-for ln, a in sorted(agg.items(), key=lambda kv: -kv[1][2])[:topn]:
-    print(f"L{ln:5d} inst {100 * a[1] / ti:5.1f}%  samples {100 * a[2] / ts:5.1f}%  smem {100 * a[3] / max(tw, 1):5.1f}%  {a[0].strip()[:110]}")
+ti, ts, tw = (sum(a[k] for a in agg.values()) for k in (1, 2, 3))
+tb = sum(a[4] for a in agg.values())
+print(f"total warp-instructions {ti}  samples {ts} (barrier {100 * tb / max(ts, 1):.1f}%)  smem wavefronts {tw}")
+k = {"samples": 2, "inst": 1, "smem": 3}[sort]
+for (f, ln), a in sorted(agg.items(), key=lambda kv: -kv[1][k])[:topn]:
+    print(f"{f[:10]:>10}:{ln:<5d} inst {100 * a[1] / ti:5.2f}%  samples {100 * a[2] / ts:5.2f}%  smem {100 * a[3] / max(tw, 1):5.2f}%  {a[0].strip()[:100]}")
