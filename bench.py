@@ -248,9 +248,10 @@ def main():
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": config,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                "api": "mjxb_step_autoreset_host (pinned host buffers)"},
+                "api": "mjxb_step_autoreset_host (pinned host buffers; one launch, action/keys streamed in behind ready flags, outputs stored into the caller's mapped buffers)"},
         "gpu_launches": 3 * args.steps,
-        "kernels": ["mjxb_step_kernel<false,32,16,16,true> (step)", "mjxb_step_kernel<false,64,24,10,true> and <false,320,176,3,true> (overflow tiers; exit at once when their list is empty)"],
+        "kernels": ["mjxb_step_kernel<false,32,16,16,true,true> (step: 32-row tile, 16 env-warps per SM, single-step instantiation)",
+                    "mjxb_step_kernel<false,64,24,10,true,false> and <false,320,176,3,true,false> (overflow tiers; exit at once when their list is empty)"],
         "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                      "traffic": traffic, "algorithmic_bytes_per_launch": ALG_BYTES_PER_STEP * n, "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 (of fallback)",
                      "algorithmic_bytes_per_env_step": ALG_BYTES_PER_STEP, "kernel_ms": kernel_ms,
