@@ -111,6 +111,8 @@ class PPOTrainer:
         self.logp_traj, self.r_traj = torch.empty(T, n, **f32), torch.empty(T, n, **f32)
         self.term_traj, self.trunc_traj = torch.empty(T, n, **f32), torch.empty(T, n, **f32)
         self.graph = None
+        self.gae_graph = None
+        self.upd = None
         self.use_graph = use_cuda_graph
         self.n_grads = sum(p.numel() for p in self.policy + [self.log_std] + self.value)
         self.timing: Dict[str, float] = {}
@@ -175,6 +177,56 @@ class PPOTrainer:
             adv[t] = carry
         return adv, adv + values[:-1]
 
+    def _minibatch_fb(self, obs_f, act_f, logp_f, ret_f, adv_f, idx, zero: bool):
+        """Losses of one minibatch (train_ppo.py:204-252) and their gradients."""
+        cfg = self.cfg
+        o, a, olp, r_, ad = obs_f[idx], act_f[idx], logp_f[idx], ret_f[idx], adv_f[idx]
+        mean = _mlp_apply(self.policy, o, self.nh_p)
+        logp = gaussian_logprob(mean, self.log_std, a)
+        ratio = torch.exp(logp - olp)
+        ad_n = (ad - ad.mean()) / (ad.std(unbiased=False) + 1e-8)
+        loss_p = -torch.minimum(ratio * ad_n, torch.clamp(ratio, 1 - cfg.clip_eps, 1 + cfg.clip_eps) * ad_n).mean()
+        entropy = 0.5 * torch.sum(1.0 + math.log(2.0 * math.pi) + 2.0 * self.log_std) / a.shape[-1]
+        loss = loss_p - cfg.ent_coef * entropy
+        if zero:
+            self.opt_p.zero_grad(set_to_none=True)
+            self.opt_v.zero_grad(set_to_none=True)
+        loss.backward()
+        v = _mlp_apply(self.value, o, self.nh_v).squeeze(-1)
+        loss_v = torch.mean((v - r_) ** 2)
+        loss_v.backward()
+
+    def _capture_update(self):
+        """Graph 1: gather + forward + backward (+ Adam when single-GPU, else + flatten of the gradients); graph 2 (sharded runs
+        only, replayed after the eager NCCL all-reduce of the flat gradient): averaged gradients back + Adam."""
+        u = self.upd
+        params = self.policy + [self.log_std] + self.value
+        torch.cuda.synchronize()
+        self.opt_p.zero_grad(set_to_none=True)
+        self.opt_v.zero_grad(set_to_none=True)
+        u["fb"] = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(u["fb"]):
+            self._minibatch_fb(u["obs"], u["act"], u["logp"], u["ret"], u["adv"], u["idx"], zero=False)
+            if self.world == 1:
+                self.opt_p.step()
+                self.opt_v.step()
+            else:
+                u["flat"].copy_(torch.cat([p.grad.reshape(-1) for p in params]))
+        if self.world > 1:
+            u["st"] = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(u["st"], pool=u["fb"].pool()):
+                o = 0
+                for p in params:
+                    p.grad.copy_(u["flat"][o:o + p.numel()].view_as(p.grad) / self.world)
+                    o += p.numel()
+                self.opt_p.step()
+                self.opt_v.step()
+        # capture does not execute: run this minibatch now
+        u["fb"].replay()
+        if self.world > 1:
+            dist.all_reduce(u["flat"])
+            u["st"].replay()
+
     def _allreduce_grads(self, params):
         if self.world == 1:
             return
@@ -200,33 +252,60 @@ class PPOTrainer:
             obs_last = self.rms.normalize(self.obs)
             stack = torch.cat([obs_norm, obs_last.unsqueeze(0)], 0).reshape((T + 1) * n, od)
             values = _mlp_apply(self.value, stack, self.nh_v).reshape(T + 1, n)
-            adv, ret = self.compute_gae(self.r_traj, values, self.term_traj, self.trunc_traj)
+            if self.use_graph:
+                # GAE's reverse scan is 2 launches per rollout step: replayed from a graph over static buffers as well
+                if self.gae_graph is None:
+                    self.values_buf = values.clone()
+                    self.compute_gae(self.r_traj, self.values_buf, self.term_traj, self.trunc_traj)      # warm-up
+                    torch.cuda.synchronize()
+                    self.gae_graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(self.gae_graph):
+                        self.gae_out = self.compute_gae(self.r_traj, self.values_buf, self.term_traj, self.trunc_traj)
+                self.values_buf.copy_(values)
+                self.gae_graph.replay()
+                adv, ret = self.gae_out
+            else:
+                adv, ret = self.compute_gae(self.r_traj, values, self.term_traj, self.trunc_traj)
         obs_f, act_f = obs_norm.reshape(T * n, od), self.act_traj.reshape(T * n, -1)
         logp_f, adv_f, ret_f = self.logp_traj.reshape(-1), adv.reshape(-1), ret.reshape(-1)
         total = T * n
         mb = min(cfg.minibatch_size, total)
         steps_per_epoch = total // mb
-        p_params = self.policy + [self.log_std]
+        if self.use_graph:
+            # the minibatch step (gather, both networks forward/backward, Adam) replays from CUDA graphs over static buffers: the
+            # eager step is ~200 launches and is bound by their dispatch, not by the GPU
+            if self.upd is None:
+                f32 = dict(dtype=torch.float32, device=self.dev)
+                self.upd = dict(obs=torch.empty(total, od, **f32), adv=torch.empty(total, **f32), ret=torch.empty(total, **f32),
+                                idx=torch.zeros(mb, dtype=torch.int64, device=self.dev), act=act_f, logp=logp_f, eager_steps=0,
+                                fb=None, st=None, flat=torch.zeros(self.n_grads, **f32))
+            u = self.upd
+            u["obs"].copy_(obs_f); u["adv"].copy_(adv_f); u["ret"].copy_(ret_f)
         for _ in range(cfg.epochs):
             perm = torch.randperm(total, device=self.dev, generator=self.gen)[: steps_per_epoch * mb].view(steps_per_epoch, mb)
             for idx in perm:
-                o, a, olp, r_, ad = obs_f[idx], act_f[idx], logp_f[idx], ret_f[idx], adv_f[idx]
-                mean = _mlp_apply(self.policy, o, self.nh_p)
-                logp = gaussian_logprob(mean, self.log_std, a)
-                ratio = torch.exp(logp - olp)
-                ad_n = (ad - ad.mean()) / (ad.std(unbiased=False) + 1e-8)
-                loss_p = -torch.minimum(ratio * ad_n, torch.clamp(ratio, 1 - cfg.clip_eps, 1 + cfg.clip_eps) * ad_n).mean()
-                entropy = 0.5 * torch.sum(1.0 + math.log(2.0 * math.pi) + 2.0 * self.log_std) / a.shape[-1]
-                loss = loss_p - cfg.ent_coef * entropy
-                self.opt_p.zero_grad(set_to_none=True)
-                self.opt_v.zero_grad(set_to_none=True)
-                loss.backward()
-                v = _mlp_apply(self.value, o, self.nh_v).squeeze(-1)
-                loss_v = torch.mean((v - r_) ** 2)
-                loss_v.backward()
-                self._allreduce_grads(p_params + self.value)
-                self.opt_p.step()
-                self.opt_v.step()
+                if not self.use_graph:
+                    self._minibatch_fb(obs_f, act_f, logp_f, ret_f, adv_f, idx, zero=True)
+                    self._allreduce_grads(self.policy + [self.log_std] + self.value)
+                    self.opt_p.step()
+                    self.opt_v.step()
+                    continue
+                u = self.upd
+                u["idx"].copy_(idx)
+                if u["eager_steps"] < 3:        # warm-up on real minibatches (cuBLAS workspaces, Adam state) before the capture
+                    self._minibatch_fb(u["obs"], u["act"], u["logp"], u["ret"], u["adv"], u["idx"], zero=True)
+                    self._allreduce_grads(self.policy + [self.log_std] + self.value)
+                    self.opt_p.step()
+                    self.opt_v.step()
+                    u["eager_steps"] += 1
+                    continue
+                if u["fb"] is None:
+                    self._capture_update()      # captures, then runs this minibatch
+                    continue
+                u["fb"].replay()
+                if self.world > 1:
+                    dist.all_reduce(u["flat"])
+                    u["st"].replay()
         ev[2].record()
         torch.cuda.synchronize()
         done = torch.maximum(self.term_traj, self.trunc_traj).sum()
