@@ -142,8 +142,17 @@ int mjxb_forward(const mjxb_model* m, int32_t n_env, mjxb_state io, const float*
  * acc += sum(pos). vel[n] in, pos[n] out (last iteration), device pointers. */
 int mjxb_speed_test(const mjxb_model* m, int32_t n_env, const float* vel, float* pos, int32_t iters, void* stream);
 
+/* launch geometry of the step kernel, for reports: cfg = {env-warps per CTA, dynamic shared memory bytes per CTA, SM count,
+ * shared memory bytes per env-warp} */
+int mjxb_launch_config(const mjxb_model* m, int32_t cfg[4]);
+
 /* Host-buffer variants (pinned or pageable host memory): H2D of the inputs, the launch, D2H of the outputs, sync.
- * The device state stays resident in a library-owned arena bound to `m` (created on first use for n_env). */
+ * The device state stays resident in a library-owned arena bound to `m` (created on first use for n_env); one caller thread
+ * per model for these entry points.
+ * Pinned (cudaHostAlloc / cudaHostRegister) buffers take the direct pipeline: ONE launch over the batch, action / keys copied in
+ * ~8 chunks on a copy stream with a ready flag per chunk that the kernel waits on, obs / reward / terminated / truncated stored
+ * by the kernel straight into the caller's buffers (visible when the call returns). Pageable buffers take a chunked three-stream
+ * H2D -> launch -> D2H pipeline. Results are identical. A chunk that never arrives (2 s) makes the call return MJXB_ECUDA. */
 int mjxb_reset_host(mjxb_model* m, int32_t n_env, const uint32_t* keys_host, float* obs_host);
 int mjxb_step_host(mjxb_model* m, int32_t n_env, const float* action_host, float* obs_host, float* reward_host,
                    float* terminated_host, float* truncated_host);

@@ -17,7 +17,7 @@ ERRORS = {0: "ok", -1: "invalid argument", -2: "bad model blob", -3: "CUDA error
 
 # every symbol include/mjxb.h declares (tests check that the built library exports all of them)
 SYMBOLS = ("mjxb_abi_version", "mjxb_blob_sizeof", "mjxb_env_config_sizeof", "mjxb_strerror", "mjxb_last_cuda_error",
-           "mjxb_model_create", "mjxb_model_destroy", "mjxb_model_dims", "mjxb_model_scratch_bytes", "mjxb_reset", "mjxb_step",
+           "mjxb_model_create", "mjxb_model_destroy", "mjxb_model_dims", "mjxb_model_scratch_bytes", "mjxb_launch_config", "mjxb_reset", "mjxb_step",
            "mjxb_step_autoreset", "mjxb_physics_step", "mjxb_forward", "mjxb_speed_test", "mjxb_reset_host", "mjxb_step_host",
            "mjxb_step_autoreset_host", "mjxb_state_get_host", "mjxb_state_set_host")
 

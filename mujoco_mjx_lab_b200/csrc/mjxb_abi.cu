@@ -108,7 +108,8 @@ int arena_ensure(mjxb_model* m, int n) {
   }
   CU(cudaMalloc(&a.ready, Arena::kReadyMax * sizeof(unsigned)));
   CU(cudaMemsetAsync(a.ready, 0, Arena::kReadyMax * sizeof(unsigned), a.stream));
-  CU(cudaHostAlloc(&a.ready_src, Arena::kReadyMax * sizeof(unsigned), cudaHostAllocDefault));
+  CU(cudaHostAlloc(&a.ready_src, (Arena::kReadyMax + 1) * sizeof(unsigned), cudaHostAllocDefault));  // [kReadyMax]: timeout flag
+  a.ready_src[Arena::kReadyMax] = 0u;
   a.epoch = 0;
   a.ready_shift = 12;  // input chunks of 2^shift envs: about 8 per step, never more than kReadyMax
   while (((n + (1 << a.ready_shift) - 1) >> a.ready_shift) > 8) a.ready_shift++;
@@ -606,6 +607,7 @@ static int step_host_impl(mjxb_model* m, int32_t n_env, const float* action_host
     sa.action = a.action; sa.keys = keys_host ? a.keys : nullptr; sa.obs = static_cast<float*>(obs_dev); sa.reward = a.reward;
     sa.terminated = a.term; sa.truncated = a.trunc;
     sa.in_ready = a.ready; sa.in_ready_shift = a.ready_shift; sa.in_ready_epoch = a.epoch;
+    sa.in_timeout = a.ready_src + Arena::kReadyMax;  // pinned: the same address is valid on the device (UVA)
     const bool obs_direct = getenv("MJXB_DIRECT_OBS") ? atoi(getenv("MJXB_DIRECT_OBS")) != 0 : true;
     const bool sc_direct = getenv("MJXB_DIRECT_SCALARS") ? atoi(getenv("MJXB_DIRECT_SCALARS")) != 0 : true;
     void *rd = nullptr, *td = nullptr, *ud = nullptr;
@@ -622,6 +624,11 @@ static int step_host_impl(mjxb_model* m, int32_t n_env, const float* action_host
     }
     CU(cudaStreamSynchronize(copy_st));
     CU(cudaStreamSynchronize(main_st));
+    if (a.ready_src[Arena::kReadyMax] != 0u) {
+      a.ready_src[Arena::kReadyMax] = 0u;
+      snprintf(g_cuda_err, sizeof(g_cuda_err), "mjxb_step_host: an input chunk did not reach the device within the bounded wait");
+      return MJXB_ECUDA;
+    }
     return MJXB_OK;
   }
   int slot = 0;

@@ -100,6 +100,7 @@ struct StepArgs {
   // host-buffer pipeline: action / keys arrive in chunks of (1 << in_ready_shift) envs while the kernel already runs; the copy
   // stream writes in_ready_epoch into in_ready[chunk] after each chunk (NULL: every input is resident at launch)
   const unsigned* in_ready; int in_ready_shift; unsigned in_ready_epoch;
+  unsigned* in_timeout;  // set to 1 (host-mapped) if a chunk did not arrive within the bounded wait
   mjxb_debug dbg;
 };
 
@@ -510,6 +511,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
           asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
           if ((int)(seen - A.in_ready_epoch) >= 0) break;
           __nanosleep(500);
+          if (spin == (1 << 22) - 1 && A.in_timeout) *A.in_timeout = 1u;
         }
       }
       __syncwarp();
