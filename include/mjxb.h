@@ -164,6 +164,18 @@ int mjxb_state_get_host(mjxb_model* m, int32_t n_env, float* qpos, float* qvel, 
 int mjxb_state_set_host(mjxb_model* m, int32_t n_env, const float* qpos, const float* qvel,
                         const float* qacc_warmstart, const float* time, const float* aux);
 
+/* ---- fused policy inference for the rollout loop (reference train_ppo.py:121-126,135-140, src/networks.py:55-61):
+ * act = mean(obs_n) + exp(log_std) * eps, logp = Gaussian log-density of act, with obs_n = clip((obs - rms_mean) / sqrt(rms_var + 1e-8), +-10)
+ * and mean = the 3 x 256 tanh MLP (obs_dim <= 64, act_dim <= 32). One launch: tcgen05 tensor cores (bf16 operands, fp32 accumulation in
+ * TMEM), activations stay on the SM. Weights are given pre-packed by mjxb_policy_pack_weight (bf16, canonical K-major core-matrix layout,
+ * zero padded: layer 0 [256 x 64], layers 1-2 [256 x 256], layer 3 [32 x 256]); biases float32. All pointers are device pointers.
+ * `mean` and `error_flag` may be NULL; *error_flag is set to 1 if a tensor-core completion was not observed (bounded wait). */
+int mjxb_policy_pack_weight(const float* w /*[k, n] row-major, x @ w*/, int32_t k, int32_t n, int32_t k_pad, int32_t n_pad,
+                            void* out_bf16 /*[n_pad * k_pad] bf16*/, void* stream);
+int mjxb_policy_act(int32_t n_env, int32_t obs_dim, int32_t act_dim, const float* obs, const float* rms_mean, const float* rms_var,
+                    const void* const* w_packed /*[4]*/, const float* const* bias /*[4]*/, const float* log_std, const float* eps,
+                    float* act, float* logp, float* mean, int32_t* error_flag, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,300 @@
+// mjxb_policy.cu -- fused policy inference for the rollout loop (reference train_ppo.py:135-140,
+// src/networks.py:55-61,105-112): obs normalisation -> 54-256-256-256-21 tanh MLP -> Gaussian sample -> log-prob, ONE launch.
+//
+// sm_100a design: a CTA owns a tile of 128 envs. The four GEMMs run on the 5th-generation tensor cores (tcgen05.mma, kind::f16 with
+// bf16 operands, fp32 accumulation in TMEM); activations never leave the SM: the epilogue reads the accumulator from TMEM
+// (tcgen05.ld), applies bias + tanh, and writes the bf16 activations straight into the canonical K-major shared-memory layout that
+// the next layer's A descriptor reads. Weights are pre-packed (mjxb_policy_pack_weight) into the canonical K-major core-matrix
+// layout, so loading a layer is a linear 16-byte-vector copy of <= 128 KB out of L2 (no TMA descriptors needed for a 0.3 MB model).
+//
+// Shared-memory operand layout (no swizzle; core matrix = 8 rows x 16 bytes, stored contiguously):
+//   A (activations, 128 rows x K):  byte(r,k) = (r%8)*16 + (r/8)*128 + (k/8)*2048 + (k%8)*2      -> SBO = 128, LBO = 2048
+//   B (weights W^T, N rows x K):     byte(n,k) = (n%8)*16 + (n/8)*(K/8)*128 + (k/8)*128 + (k%8)*2 -> SBO = 16*K, LBO = 128
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "mjxb.h"
+
+namespace mjxbp {
+
+constexpr int kTile = 128;      // envs per CTA = MMA M
+constexpr int kHid = 256;       // hidden width = MMA N of the hidden layers
+constexpr int kInPad = 64;      // obs_dim 54 padded to a multiple of 16
+constexpr int kOutPad = 32;     // action dim 21 padded to a multiple of 16
+constexpr int kThreads = 256;
+constexpr int kABytes = kTile * kHid * 2;        // 64 KB
+constexpr int kWBytes = kHid * kHid * 2;         // 128 KB (largest layer)
+constexpr int kSmemBytes = kABytes + kWBytes + 2 * kHid * 4 + 64;   // + double-buffered bias + mbarrier + TMEM slot
+constexpr uint32_t kTmemCols = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version 1 (sm_100); base offset 0, no swizzle
+  return d;
+}
+
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128
+__device__ __forceinline__ uint32_t umma_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+struct PolicyArgs {
+  int n_env, obs_dim, act_dim;
+  const float* obs;        // [n, obs_dim]
+  const float* rms_mean;   // [obs_dim] or NULL (no normalisation)
+  const float* rms_var;    // [obs_dim]
+  const void* w[4];        // packed bf16 weights (mjxb_policy_pack_weight)
+  const float* b[4];       // biases, float32
+  const float* log_std;    // [act_dim]
+  const float* eps;        // [n, act_dim] standard normal noise
+  float* act;              // [n, act_dim]
+  float* logp;             // [n]
+  float* mean;             // [n, act_dim] or NULL
+  int* error;              // device flag: set to 1 if an MMA completion was not observed within the bounded wait
+};
+
+__global__ void __launch_bounds__(kThreads, 1) policy_act_kernel(PolicyArgs P) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* sA = smem;
+  unsigned char* sW = smem + kABytes;
+  float* sBias2 = reinterpret_cast<float*>(smem + kABytes + kWBytes);   // [2][kHid]: layer l+1 is staged while layer l's epilogue reads
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + kABytes + kWBytes + 2 * kHid * 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kABytes + kWBytes + 2 * kHid * 4 + 16);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = 32 * (warp & 3) + lane;   // TMEM lane == env row of the tile (a warp may only touch lanes 32*(warp%4)..+31)
+  const int half = warp >> 2;               // which half of the columns this thread handles
+  const int env = blockIdx.x * kTile + row;
+  const bool live = env < P.n_env;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(mbar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  // linear 16-byte cp.async copy of a layer's packed weight image into sW (+ its bias into the parity buffer): all 32 vectors of a
+  // thread are in flight at once, and the copy of layer l+1 overlaps the epilogue of layer l (sW is free once layer l's MMAs retired)
+  auto stage_layer = [&](int layer) {
+    const int K = (layer == 0) ? kInPad : kHid;
+    const int N = (layer == 3) ? kOutPad : kHid;
+    const char* src = reinterpret_cast<const char*>(P.w[layer]);
+    const uint32_t dst = smem_u32(sW);
+    const int nvec = N * K * 2 / 16;
+    for (int i = tid; i < nvec; i += kThreads)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst + 16u * (uint32_t)i), "l"(src + 16 * (size_t)i) : "memory");
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    float* sb = sBias2 + (layer & 1) * kHid;
+    const int nb = (layer == 3) ? P.act_dim : kHid;
+    for (int i = tid; i < kHid; i += kThreads) sb[i] = (i < nb) ? P.b[layer][i] : 0.0f;
+  };
+
+  stage_layer(0);
+  // ---- layer-0 A operand: normalised observations, bf16, K padded 54 -> 64 (this thread: features 32*half .. 32*half+31)
+  {
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const int k0 = 32 * half + 8 * c;
+      __align__(16) __nv_bfloat162 pk[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        float x[2];
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+          const int k = k0 + 2 * j + t;
+          float val = 0.0f;
+          if (live && k < P.obs_dim) {
+            val = P.obs[(size_t)env * P.obs_dim + k];
+            if (P.rms_mean) val = fminf(fmaxf((val - P.rms_mean[k]) / sqrtf(P.rms_var[k] + 1e-8f), -10.0f), 10.0f);
+          }
+          x[t] = val;
+        }
+        pk[j] = __floats2bfloat162_rn(x[0], x[1]);
+      }
+      *reinterpret_cast<int4*>(sA + (row & 7) * 16 + (row >> 3) * 128 + (k0 >> 3) * 2048) = *reinterpret_cast<const int4*>(pk);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem_d = *tmem_slot;
+
+  float out_mean[kOutPad];
+#pragma unroll
+  for (int j = 0; j < kOutPad; j++) out_mean[j] = 0.0f;
+#pragma unroll 1
+  for (int layer = 0; layer < 4; layer++) {
+    float* sBias = sBias2 + (layer & 1) * kHid;
+    const int K = (layer == 0) ? kInPad : kHid;
+    const int N = (layer == 3) ? kOutPad : kHid;
+    // ---- this layer's weights and bias were put in flight (cp.async) before the previous epilogue: land them
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy smem writes -> visible to the tensor-core proxy
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 0 && lane == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      const uint32_t idesc = umma_idesc(N);
+      const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sW);
+      for (int ks = 0; ks < K / 16; ks++) {
+        const uint64_t ad = umma_desc(a0 + ks * 2 * 2048, 2048, 128);
+        const uint64_t bd = umma_desc(b0 + ks * 2 * 128, 128, 16 * K);
+        umma_bf16(tmem_d, ad, bd, idesc, ks > 0 ? 1u : 0u);
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(mbar)) : "memory");
+    }
+    {  // wait for the accumulator (phase parity alternates per layer); bounded so that a fault cannot hang the device
+      const uint32_t parity = layer & 1;
+      uint32_t ok = 0;
+      for (int spin = 0; spin < (1 << 22) && !ok; spin++) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(mbar)), "r"(parity)
+            : "memory");
+      }
+      if (!ok && P.error) *P.error = 1;
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    if (layer < 3) stage_layer(layer + 1);
+    // ---- epilogue: this thread's row, its half of the columns
+    if (layer < 3) {
+#pragma unroll 1
+      for (int cb = 0; cb < kHid / 2; cb += 32) {
+        const int col0 = half * (kHid / 2) + cb;
+        uint32_t v[32];
+        tmem_ld32(tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)col0, v);
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          __align__(16) __nv_bfloat162 pk[4];
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const int cc = 8 * c + 2 * j;
+            const float y0 = tanh_fast(__uint_as_float(v[cc]) + sBias[col0 + cc]);
+            const float y1 = tanh_fast(__uint_as_float(v[cc + 1]) + sBias[col0 + cc + 1]);
+            pk[j] = __floats2bfloat162_rn(y0, y1);
+          }
+          const int k0 = col0 + 8 * c;
+          *reinterpret_cast<int4*>(sA + (row & 7) * 16 + (row >> 3) * 128 + (k0 >> 3) * 2048) = *reinterpret_cast<const int4*>(pk);
+        }
+      }
+    } else if (half == 0) {
+      uint32_t v[32];
+      tmem_ld32(tmem_d + ((uint32_t)(32 * (warp & 3)) << 16), v);
+#pragma unroll
+      for (int j = 0; j < kOutPad; j++) out_mean[j] = __uint_as_float(v[j]) + sBias[j];
+    }
+  }
+  // ---- sample, log-prob (train_ppo.py:121-126,135-140), store
+  if (half == 0 && live) {
+    float lp = 0.0f;
+#pragma unroll
+    for (int j = 0; j < kOutPad; j++) {
+      if (j < P.act_dim) {
+        const float ls = P.log_std[j];
+        const float e = P.eps[(size_t)env * P.act_dim + j];
+        const float a = out_mean[j] + __expf(ls) * e;
+        P.act[(size_t)env * P.act_dim + j] = a;
+        if (P.mean) P.mean[(size_t)env * P.act_dim + j] = out_mean[j];
+        const float d = a - out_mean[j];
+        lp += d * d / __expf(2.0f * ls) + 2.0f * ls + 1.8378770664093453f;
+      }
+    }
+    P.logp[env] = -0.5f * lp;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "r"(kTmemCols) : "memory");
+  }
+}
+
+// W [K, N] row-major float32 (x @ W convention) -> bf16 image of B = W^T in the canonical K-major layout, zero padded to [Np, Kp]
+__global__ void pack_weight_kernel(const float* __restrict__ w, int K, int N, int Kp, int Np, __nv_bfloat16* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Np * Kp) return;
+  const int n = idx / Kp, k = idx % Kp;
+  const float v = (n < N && k < K) ? w[(size_t)k * N + n] : 0.0f;
+  const size_t byte = (size_t)(n & 7) * 16 + (size_t)(n >> 3) * (Kp / 8) * 128 + (size_t)(k >> 3) * 128 + (size_t)(k & 7) * 2;
+  out[byte / 2] = __float2bfloat16_rn(v);
+}
+
+}  // namespace mjxbp
+
+extern "C" {
+
+int mjxb_policy_pack_weight(const float* w, int32_t k, int32_t n, int32_t k_pad, int32_t n_pad, void* out_bf16, void* stream) {
+  if (!w || !out_bf16 || k <= 0 || n <= 0 || k_pad < k || n_pad < n || (k_pad % 16) || (n_pad % 16)) return MJXB_EINVAL;
+  const int total = n_pad * k_pad;
+  mjxbp::pack_weight_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, k, n, k_pad, n_pad, (__nv_bfloat16*)out_bf16);
+  return cudaGetLastError() == cudaSuccess ? MJXB_OK : MJXB_ECUDA;
+}
+
+int mjxb_policy_act(int32_t n_env, int32_t obs_dim, int32_t act_dim, const float* obs, const float* rms_mean, const float* rms_var,
+                    const void* const* w_packed, const float* const* bias, const float* log_std, const float* eps, float* act,
+                    float* logp, float* mean, int32_t* error_flag, void* stream) {
+  if (n_env <= 0 || !obs || !w_packed || !bias || !log_std || !eps || !act || !logp) return MJXB_EINVAL;
+  if (obs_dim <= 0 || obs_dim > mjxbp::kInPad || act_dim <= 0 || act_dim > mjxbp::kOutPad) return MJXB_EUNSUPPORTED;
+  if ((rms_mean == nullptr) != (rms_var == nullptr)) return MJXB_EINVAL;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(mjxbp::policy_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mjxbp::kSmemBytes) != cudaSuccess) {
+      cudaGetLastError();
+      return MJXB_ECUDA;
+    }
+    attr_set = true;
+  }
+  mjxbp::PolicyArgs P;
+  P.n_env = n_env; P.obs_dim = obs_dim; P.act_dim = act_dim; P.obs = obs; P.rms_mean = rms_mean; P.rms_var = rms_var;
+  for (int i = 0; i < 4; i++) {
+    if (!w_packed[i] || !bias[i]) return MJXB_EINVAL;
+    P.w[i] = w_packed[i]; P.b[i] = bias[i];
+  }
+  P.log_std = log_std; P.eps = eps; P.act = act; P.logp = logp; P.mean = mean; P.error = error_flag;
+  const int grid = (n_env + mjxbp::kTile - 1) / mjxbp::kTile;
+  mjxbp::policy_act_kernel<<<grid, mjxbp::kThreads, mjxbp::kSmemBytes, (cudaStream_t)stream>>>(P);
+  return cudaGetLastError() == cudaSuccess ? MJXB_OK : MJXB_ECUDA;
+}
+
+}  // extern "C"

@@ -65,7 +65,7 @@ def create_env_functions(sys: Model, cfg, q0, nq: int, nv: int) -> Tuple[Callabl
                                     obs.data_ptr(), None, _stream()), "mjxb_reset")
         return (d, aux), obs
 
-    def _step(state: EnvState, action, keys=None, inplace=False):
+    def _step(state: EnvState, action, keys=None, inplace=False, out=None):
         d, aux = state
         n = d.qpos.shape[0]
         action = _f32(action, (n, nu))
@@ -75,8 +75,13 @@ def create_env_functions(sys: Model, cfg, q0, nq: int, nv: int) -> Tuple[Callabl
             d2, aux2 = Data(qpos, qvel, warm, time), aux
         else:
             d2, aux2 = _alloc_state(n)
-        obs = torch.empty(n, od, **f32)
-        reward, term, trunc = torch.empty(n, **f32), torch.empty(n, **f32), torch.empty(n, **f32)
+        if out is not None and not all(t.is_contiguous() for t in out):
+            raise ValueError("output buffers must be contiguous")
+        if out is not None:         # caller-owned output buffers (obs [n, obs_dim], reward / terminated / truncated [n]), e.g. rollout slices
+            obs, reward, term, trunc = (_f32(out[0], (n, od)), _f32(out[1], (n,)), _f32(out[2], (n,)), _f32(out[3], (n,)))
+        else:
+            obs = torch.empty(n, od, **f32)
+            reward, term, trunc = torch.empty(n, **f32), torch.empty(n, **f32), torch.empty(n, **f32)
         sin, sout = state_c(qpos, qvel, warm, time, aux), state_c(d2.qpos, d2.qvel, d2.qacc_warmstart, d2.time, aux2)
         with torch.cuda.device(dev):
             if keys is None:
@@ -92,7 +97,7 @@ def create_env_functions(sys: Model, cfg, q0, nq: int, nv: int) -> Tuple[Callabl
     def v_step(state: EnvState, action):
         return _step(state, action)
 
-    v_step.autoreset = lambda state, action, keys, inplace=False: _step(state, action, keys, inplace)
+    v_step.autoreset = lambda state, action, keys, inplace=False, out=None: _step(state, action, keys, inplace, out)
     v_step.sys = env_sys
 
     def single_reset(key):

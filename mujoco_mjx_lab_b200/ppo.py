@@ -82,7 +82,8 @@ class RMS:  # reference src/training_utils.py:20-56
 
 
 class PPOTrainer:
-    def __init__(self, cfg: PPOConfig, v_reset, v_step, num_envs_local: int, seed: int = 42, use_cuda_graph: bool = True):
+    def __init__(self, cfg: PPOConfig, v_reset, v_step, num_envs_local: int, seed: int = 42, use_cuda_graph: bool = True,
+                 use_fused_policy: bool = True):
         self.cfg, self.v_reset, self.v_step = cfg, v_reset, v_step
         self.sys = v_step.sys
         self.dev = self.sys.device
@@ -110,6 +111,12 @@ class PPOTrainer:
         self.obs_traj, self.act_traj = torch.empty(T, n, od, **f32), torch.empty(T, n, nu, **f32)
         self.logp_traj, self.r_traj = torch.empty(T, n, **f32), torch.empty(T, n, **f32)
         self.term_traj, self.trunc_traj = torch.empty(T, n, **f32), torch.empty(T, n, **f32)
+        self.fused = None
+        if use_fused_policy and self.dev.type == "cuda":
+            from . import policy as _policy
+            flat = [p.detach() for p in self.policy]
+            if _policy.supported(flat, od, nu) and all(a == "tanh" for _, a in cfg.policy_hidden_layer_specs):
+                self.fused = _policy.FusedPolicy(flat, self.log_std.detach(), od, nu)
         self.graph = None
         self.gae_graph = None
         self.upd = None
@@ -119,20 +126,25 @@ class PPOTrainer:
 
     # ---------------------------------------------------------------- rollout (train_ppo.py:128-169)
     def _rollout_body(self):
+        if self.fused is not None:
+            self.fused.pack()                                           # bf16 image of the current policy weights (4 tiny kernels)
         for t in range(self.T):
-            obs_n = self.rms.normalize(self.obs)
-            mean = _mlp_apply(self.policy, obs_n, self.nh_p)
-            eps = torch.randn(mean.shape, device=self.dev)              # default CUDA generator: graph-capture safe
-            act = mean + torch.exp(self.log_std) * eps
             keys = torch.randint(-2 ** 31, 2 ** 31 - 1, (self.n, 2), device=self.dev, dtype=torch.int32)
             self.obs_traj[t].copy_(self.obs)
-            self.act_traj[t].copy_(act)
-            self.logp_traj[t].copy_(gaussian_logprob(mean, self.log_std, act))
-            _, obs, r, te, tr = self.v_step.autoreset(self.state, act, keys, inplace=True)
-            self.r_traj[t].copy_(r)
-            self.term_traj[t].copy_(te)
-            self.trunc_traj[t].copy_(tr)
-            self.obs.copy_(obs)
+            if self.fused is not None:
+                # normalise -> MLP -> sample -> log-prob in one tcgen05 launch, written straight into the trajectory buffers
+                eps = torch.randn(self.n, self.act_traj.shape[-1], device=self.dev)
+                act, _ = self.fused.act(self.obs, eps, self.rms.mean, self.rms.var, act_out=self.act_traj[t], logp_out=self.logp_traj[t])
+            else:
+                obs_n = self.rms.normalize(self.obs)
+                mean = _mlp_apply(self.policy, obs_n, self.nh_p)
+                eps = torch.randn(mean.shape, device=self.dev)          # default CUDA generator: graph-capture safe
+                act = mean + torch.exp(self.log_std) * eps
+                self.act_traj[t].copy_(act)
+                self.logp_traj[t].copy_(gaussian_logprob(mean, self.log_std, act))
+            # the step writes the next observation and this step's reward / terminated / truncated where the trainer keeps them
+            self.v_step.autoreset(self.state, act, keys, inplace=True,
+                                  out=(self.obs, self.r_traj[t], self.term_traj[t], self.trunc_traj[t]))
 
     @torch.no_grad()
     def collect_rollout(self):
@@ -347,5 +359,5 @@ def time_ppo(num_envs_local: int, rollout_length: int, iters: int = 5, warmup: i
     res.update(wall_iter_ms=wall, envs_per_gpu=num_envs_local, rollout_length=rollout_length, world=tr.world,
                env_steps_per_sec=num_envs_local * tr.world * rollout_length / (wall * 1e-3), minibatches=last.get("minibatches"),
                allreduce_floats_per_minibatch=last.get("allreduce_floats"), train_return_avg=last.get("train_return_avg"),
-               cuda_graph=bool(use_cuda_graph))
+               cuda_graph=bool(use_cuda_graph), fused_policy_kernel=tr.fused is not None)
     return res
