@@ -176,6 +176,16 @@ int mjxb_policy_act(int32_t n_env, int32_t obs_dim, int32_t act_dim, const float
                     const void* const* w_packed /*[4]*/, const float* const* bias /*[4]*/, const float* log_std, const float* eps,
                     float* act, float* logp, float* mean, int32_t* error_flag, void* stream);
 
+/* Learner backward helper for y = tanh(x W + b): dz = dy * (1 - y^2) and db += column sums of dz in one pass over [n, c] row-major
+ * arrays (y == NULL: plain linear layer, dz is not written and db += column sums of dy). db must be zeroed by the caller. */
+int mjxb_tanh_bwd_colsum(int32_t n, int32_t c, const float* dy, const float* y, float* dz, float* db_zeroed, void* stream);
+
+/* Generalised advantage estimation over a rollout (reference train_ppo.py:171-202): delta_t = r_t + gamma v_{t+1} (1 - terminated_t) - v_t,
+ * adv_t = delta_t + gamma lam (1 - max(terminated_t, truncated_t)) adv_{t+1}, ret_t = adv_t + v_t. reward / terminated / truncated /
+ * advantage / ret are [rollout_length, n_env], value is [rollout_length + 1, n_env]; device pointers, one launch. */
+int mjxb_gae(int32_t rollout_length, int32_t n_env, const float* reward, const float* value, const float* terminated,
+             const float* truncated, float gamma, float lam, float* advantage, float* ret, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,7 +19,7 @@ ERRORS = {0: "ok", -1: "invalid argument", -2: "bad model blob", -3: "CUDA error
 SYMBOLS = ("mjxb_abi_version", "mjxb_blob_sizeof", "mjxb_env_config_sizeof", "mjxb_strerror", "mjxb_last_cuda_error",
            "mjxb_model_create", "mjxb_model_destroy", "mjxb_model_dims", "mjxb_model_scratch_bytes", "mjxb_launch_config", "mjxb_reset", "mjxb_step",
            "mjxb_step_autoreset", "mjxb_physics_step", "mjxb_forward", "mjxb_speed_test", "mjxb_reset_host", "mjxb_step_host",
-           "mjxb_step_autoreset_host", "mjxb_state_get_host", "mjxb_state_set_host", "mjxb_policy_pack_weight", "mjxb_policy_act")
+           "mjxb_step_autoreset_host", "mjxb_state_get_host", "mjxb_state_set_host", "mjxb_policy_pack_weight", "mjxb_policy_act", "mjxb_gae", "mjxb_tanh_bwd_colsum")
 
 
 class MjxbError(RuntimeError):
@@ -78,6 +78,8 @@ def lib() -> C.CDLL:
     L.mjxb_state_get_host.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     L.mjxb_state_set_host.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     L.mjxb_policy_pack_weight.argtypes = [vp, i32, i32, i32, i32, vp, vp]
+    L.mjxb_tanh_bwd_colsum.argtypes = [i32, i32, vp, vp, vp, vp, vp]
+    L.mjxb_gae.argtypes = [i32, i32, vp, vp, vp, vp, C.c_float, C.c_float, vp, vp, vp]
     L.mjxb_policy_act.argtypes = [i32, i32, i32, vp, vp, vp, C.POINTER(vp), C.POINTER(vp), vp, vp, vp, vp, vp, vp, vp]
     if L.mjxb_abi_version() != 1:
         raise MjxbError("libmjxb.so ABI version mismatch")

@@ -260,9 +260,68 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int K, int N, in
   out[byte / 2] = __float2bfloat16_rn(v);
 }
 
+// GAE reverse scan (reference train_ppo.py:171-202): one thread per env walks the rollout backwards; the loads of a step do not depend
+// on the carried advantage, so the unrolled loop keeps eight steps of loads in flight (coalesced across envs)
+__global__ void gae_kernel(int T, int n, const float* __restrict__ r, const float* __restrict__ v, const float* __restrict__ te,
+                           const float* __restrict__ tr, float gamma, float lam, float* __restrict__ adv, float* __restrict__ ret) {
+  const int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= n) return;
+  float carry = 0.0f, vnext = v[(size_t)T * n + env];
+#pragma unroll 8
+  for (int t = T - 1; t >= 0; t--) {
+    const size_t i = (size_t)t * n + env;
+    const float vt = v[i], term = te[i], trunc = tr[i];
+    const float delta = r[i] + gamma * vnext * (1.0f - term) - vt;
+    carry = delta + gamma * lam * (1.0f - fmaxf(term, trunc)) * carry;
+    adv[i] = carry;
+    ret[i] = carry + vt;
+    vnext = vt;
+  }
+}
+
+// Learner backward helper: dz = dy * (1 - y^2) (tanh backward; y == NULL: dz = dy, no write) fused with the bias gradient
+// db[c] += sum_rows dz[:, c]. Thread j owns column j of a row block (coalesced across the CTA); one atomicAdd per column per CTA.
+__global__ void tanh_bwd_colsum_kernel(int n, int c, const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dz,
+                                       float* __restrict__ db) {
+  const int rows_per_cta = (n + gridDim.x - 1) / gridDim.x;
+  const int r0 = blockIdx.x * rows_per_cta, r1 = min(n, r0 + rows_per_cta);
+  for (int col = threadIdx.x; col < c; col += blockDim.x) {
+    float acc = 0.0f;
+#pragma unroll 8
+    for (int r = r0; r < r1; r++) {
+      const size_t i = (size_t)r * c + col;
+      float g = dy[i];
+      if (y != nullptr) {
+        const float t = y[i];
+        g *= 1.0f - t * t;
+        dz[i] = g;
+      }
+      acc += g;
+    }
+    if (r1 > r0) atomicAdd(db + col, acc);
+  }
+}
+
 }  // namespace mjxbp
 
 extern "C" {
+
+int mjxb_tanh_bwd_colsum(int32_t n, int32_t c, const float* dy, const float* y, float* dz, float* db_zeroed, void* stream) {
+  if (n <= 0 || c <= 0 || !dy || !db_zeroed || (y != nullptr && dz == nullptr)) return MJXB_EINVAL;
+  int grid = (n + 63) / 64;
+  if (grid > 148 * 8) grid = 148 * 8;
+  const int threads = c >= 256 ? 256 : ((c + 31) / 32) * 32;
+  mjxbp::tanh_bwd_colsum_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(n, c, dy, y, dz, db_zeroed);
+  return cudaGetLastError() == cudaSuccess ? MJXB_OK : MJXB_ECUDA;
+}
+
+int mjxb_gae(int32_t rollout_length, int32_t n_env, const float* reward, const float* value, const float* terminated,
+             const float* truncated, float gamma, float lam, float* advantage, float* ret, void* stream) {
+  if (rollout_length <= 0 || n_env <= 0 || !reward || !value || !terminated || !truncated || !advantage || !ret) return MJXB_EINVAL;
+  mjxbp::gae_kernel<<<(n_env + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rollout_length, n_env, reward, value, terminated, truncated,
+                                                                           gamma, lam, advantage, ret);
+  return cudaGetLastError() == cudaSuccess ? MJXB_OK : MJXB_ECUDA;
+}
 
 int mjxb_policy_pack_weight(const float* w, int32_t k, int32_t n, int32_t k_pad, int32_t n_pad, void* out_bf16, void* stream) {
   if (!w || !out_bf16 || k <= 0 || n <= 0 || k_pad < k || n_pad < n || (k_pad % 16) || (n_pad % 16)) return MJXB_EINVAL;

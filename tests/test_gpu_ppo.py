@@ -30,7 +30,10 @@ def test_gae_matches_numpy(env):
     r, v = torch.randn(T, n, device="cuda", generator=g), torch.randn(T + 1, n, device="cuda", generator=g)
     te = (torch.rand(T, n, device="cuda", generator=g) < 0.1).float()
     trn = (torch.rand(T, n, device="cuda", generator=g) < 0.1).float()
-    adv, ret = tr.compute_gae(r, v, te, trn)
+    adv, ret = tr.compute_gae(r, v, te, trn)                        # mjxb_gae kernel
+    adv_t, ret_t = tr.compute_gae(r, v, te, trn, force_torch=True)  # the torch scan it replaces
+    torch.testing.assert_close(adv, adv_t, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(ret, ret_t, rtol=1e-5, atol=1e-5)
     rn, vn, ten, trnn = (x.double().cpu().numpy() for x in (r, v, te, trn))
     gam, lam = tr.cfg.gamma, tr.cfg.lam
     ref, carry = np.zeros((T, n)), np.zeros(n)
@@ -57,4 +60,23 @@ def test_graph_update_equals_eager(env):
         assert np.isfinite(ra["train_return_avg"]) and ra["minibatches"] == 16
         for pa, pb in zip(a.policy + [a.log_std] + a.value, b.policy + [b.log_std] + b.value):
             torch.testing.assert_close(pa, pb, rtol=2e-3, atol=2e-4)
-    assert a.upd["fb"] is not None and a.gae_graph is not None
+    assert a.upd["fb"] is not None
+
+
+def test_linear_act_backward_matches_autograd():
+    """The learner's linear(+tanh) layer with the fused tanh-backward / bias-gradient kernel gives torch autograd's gradients."""
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for n, k, c, act in [(1000, 54, 256, True), (4097, 256, 256, True), (3000, 256, 21, False), (512, 256, 1, False)]:
+        x = torch.randn(n, k, device="cuda", generator=g, requires_grad=True)
+        w = (torch.randn(k, c, device="cuda", generator=g) * 0.1).requires_grad_()
+        b = torch.randn(c, device="cuda", generator=g).requires_grad_()
+        up = torch.randn(n, c, device="cuda", generator=g)
+        y = ppo_mod._LinearAct.apply(x, w, b, act)
+        gx, gw, gb = torch.autograd.grad((y * up).sum(), (x, w, b))
+        y2 = torch.addmm(b, x, w)
+        y2 = torch.tanh(y2) if act else y2
+        rx, rw, rb = torch.autograd.grad((y2 * up).sum(), (x, w, b))
+        torch.testing.assert_close(y, y2, rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(gx, rx, rtol=1e-3, atol=1e-3)
+        torch.testing.assert_close(gw, rw, rtol=1e-3, atol=2e-2)        # TF32 products summed over n rows
+        torch.testing.assert_close(gb, rb, rtol=1e-4, atol=1e-2)
