@@ -63,7 +63,13 @@ class _LinearAct(torch.autograd.Function):
                                                    dz.data_ptr() if ctx.act else None, db.data_ptr(),
                                                    C.c_void_p(torch.cuda.current_stream().cuda_stream)), "mjxb_tanh_bwd_colsum")
         dx = dz @ w.t() if ctx.needs_input_grad[0] else None
-        dw = x.t() @ dz
+        # weight gradient = [k, n] x [n, c] with a tiny output and n in the tens of thousands: cuBLAS's own choice for that shape runs at
+        # ~90 TFLOP/s (tools/wgrad_probe.py: 100-118 us); an explicit 64-way split over the rows as one batched GEMM + sum takes 43 us
+        split = 64
+        if n >= 8192 and n % split == 0:
+            dw = torch.bmm(x.view(split, n // split, x.shape[1]).transpose(1, 2), dz.view(split, n // split, c)).sum(0)
+        else:
+            dw = x.t() @ dz
         return dx, dw, db, None
 
 

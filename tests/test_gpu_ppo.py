@@ -66,7 +66,8 @@ def test_graph_update_equals_eager(env):
 def test_linear_act_backward_matches_autograd():
     """The learner's linear(+tanh) layer with the fused tanh-backward / bias-gradient kernel gives torch autograd's gradients."""
     g = torch.Generator(device="cuda").manual_seed(1)
-    for n, k, c, act in [(1000, 54, 256, True), (4097, 256, 256, True), (3000, 256, 21, False), (512, 256, 1, False)]:
+    for n, k, c, act in [(1000, 54, 256, True), (4097, 256, 256, True), (3000, 256, 21, False), (512, 256, 1, False),
+                         (16384, 256, 256, True), (8192, 54, 256, False)]:      # the last two take the split-row weight gradient
         x = torch.randn(n, k, device="cuda", generator=g, requires_grad=True)
         w = (torch.randn(k, c, device="cuda", generator=g) * 0.1).requires_grad_()
         b = torch.randn(c, device="cuda", generator=g).requires_grad_()
@@ -78,5 +79,5 @@ def test_linear_act_backward_matches_autograd():
         rx, rw, rb = torch.autograd.grad((y2 * up).sum(), (x, w, b))
         torch.testing.assert_close(y, y2, rtol=1e-5, atol=1e-5)
         torch.testing.assert_close(gx, rx, rtol=1e-3, atol=1e-3)
-        torch.testing.assert_close(gw, rw, rtol=1e-3, atol=2e-2)        # TF32 products summed over n rows
+        torch.testing.assert_close(gw, rw, rtol=1e-3, atol=5e-2)        # TF32 products summed over n rows
         torch.testing.assert_close(gb, rb, rtol=1e-4, atol=1e-2)
