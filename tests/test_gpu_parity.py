@@ -306,6 +306,43 @@ def test_host_buffer_api_pinned_direct(model, env):
     assert torch.equal(qpos_h, state[0].qpos.cpu())
 
 
+def test_host_step_without_autoreset_and_odd_sizes(model, env):
+    """mjxb_step_host (no auto-reset) through pinned buffers, at sizes around one launch wave and a single env."""
+    from mujoco_mjx_lab_b200 import _lib
+    v_reset, v_step = env[8], env[9]
+    L, h = _lib.lib(), v_step.sys.handle
+    for n in (1, 2369, 4097):
+        keys = helpers.ppo_keys(3, n)
+        pin = lambda *shape: torch.zeros(*shape, dtype=torch.float32).pin_memory()
+        obs_h, r_h, te_h, tr_h, act_h = pin(n, 54), pin(n), pin(n), pin(n), pin(n, 21)
+        keys_h = torch.from_numpy(keys.view(np.int32).copy()).pin_memory()
+        _lib.check(L.mjxb_reset_host(h, n, keys_h.data_ptr(), obs_h.data_ptr()))
+        state, obs = v_reset(keys)
+        act_h.copy_(torch.from_numpy(np.random.default_rng(n).uniform(-1, 1, (n, 21)).astype(np.float32)))
+        for _ in range(2):
+            _lib.check(L.mjxb_step_host(h, n, act_h.data_ptr(), obs_h.data_ptr(), r_h.data_ptr(), te_h.data_ptr(), tr_h.data_ptr()))
+            state, obs, r, te, tr = v_step(state, act_h.cuda())
+        assert torch.equal(obs_h, obs.cpu()) and torch.equal(r_h, r.cpu()) and torch.equal(te_h, te.cpu()) and torch.equal(tr_h, tr.cpu())
+
+
+def test_step_into_caller_buffers(env):
+    """v_step.autoreset(..., out=(obs, reward, terminated, truncated)) writes the same bits into caller-owned buffers (rollout slices)."""
+    v_reset, v_step = env[8], env[9]
+    n = 700
+    state, obs0 = v_reset(helpers.ppo_keys(11, n))
+    act = torch.rand(n, 21, device="cuda") * 2 - 1
+    rk = helpers.ppo_keys(12, n)
+    s1, o1, r1, te1, tr1 = v_step.autoreset(state, act, rk)
+    traj = torch.zeros(3, 4, n, device="cuda")
+    obs_buf = torch.zeros(n, 54, device="cuda")
+    s2, o2, r2, te2, tr2 = v_step.autoreset(state, act, rk, out=(obs_buf, traj[0, 1], traj[1, 1], traj[2, 1]))
+    assert o2.data_ptr() == obs_buf.data_ptr() and r2.data_ptr() == traj[0, 1].data_ptr()
+    assert torch.equal(o1, obs_buf) and torch.equal(r1, traj[0, 1]) and torch.equal(te1, traj[1, 1]) and torch.equal(tr1, traj[2, 1])
+    assert torch.equal(s1[0].qpos, s2[0].qpos)
+    with pytest.raises(ValueError):
+        v_step.autoreset(state, act, rk, out=(obs_buf, traj[0, :, 0], traj[1, 1], traj[2, 1]))      # non-contiguous slice
+
+
 def test_argument_errors(env):
     from mujoco_mjx_lab_b200 import _lib
     v_reset, v_step = env[8], env[9]
