@@ -146,10 +146,14 @@ class PPOTrainer:
         keys = torch.from_numpy(parallel.rank_keys(seed, self.rank, self.n).view(np.int32)).to(self.dev)
         (d, aux), obs = v_reset(keys)
         self.state = (Data(d.qpos, d.qvel, d.qacc_warmstart, d.time), aux)
-        self.obs = obs
         f32 = dict(dtype=torch.float32, device=self.dev)
         T, n = self.T, self.n
-        self.obs_traj, self.act_traj = torch.empty(T, n, od, **f32), torch.empty(T, n, nu, **f32)
+        # observations of a rollout live in one [T + 1, n, obs_dim] buffer: the step writes slot t + 1 directly (no per-step copy);
+        # `obs` (the current observation) is the last slot, `obs_traj` the first T
+        self.obs_all = torch.empty(T + 1, n, od, **f32)
+        self.obs_traj, self.obs = self.obs_all[:T], self.obs_all[T]
+        self.obs.copy_(obs)
+        self.act_traj = torch.empty(T, n, nu, **f32)
         self.logp_traj, self.r_traj = torch.empty(T, n, **f32), torch.empty(T, n, **f32)
         self.term_traj, self.trunc_traj = torch.empty(T, n, **f32), torch.empty(T, n, **f32)
         self.fused = None
@@ -168,15 +172,21 @@ class PPOTrainer:
     def _rollout_body(self):
         if self.fused is not None:
             self.fused.pack()                                           # bf16 image of the current policy weights (4 tiny kernels)
+        nu = self.act_traj.shape[-1]
+        # reset keys (and, when they fit in 512 MB, the sampling noise) of the whole rollout are drawn by one launch each
+        keys_all = torch.randint(-2 ** 31, 2 ** 31 - 1, (self.T, self.n, 2), device=self.dev, dtype=torch.int32)
+        eps_all = torch.randn(self.T, self.n, nu, device=self.dev) if self.T * self.n * nu * 4 <= (512 << 20) else None
+        self.obs_all[0].copy_(self.obs)
         for t in range(self.T):
-            keys = torch.randint(-2 ** 31, 2 ** 31 - 1, (self.n, 2), device=self.dev, dtype=torch.int32)
-            self.obs_traj[t].copy_(self.obs)
+            keys = keys_all[t]
+            obs_t = self.obs_all[t]
+            obs_next = self.obs if t == self.T - 1 else self.obs_all[t + 1]
             if self.fused is not None:
                 # normalise -> MLP -> sample -> log-prob in one tcgen05 launch, written straight into the trajectory buffers
-                eps = torch.randn(self.n, self.act_traj.shape[-1], device=self.dev)
-                act, _ = self.fused.act(self.obs, eps, self.rms.mean, self.rms.var, act_out=self.act_traj[t], logp_out=self.logp_traj[t])
+                eps = eps_all[t] if eps_all is not None else torch.randn(self.n, nu, device=self.dev)
+                act, _ = self.fused.act(obs_t, eps, self.rms.mean, self.rms.var, act_out=self.act_traj[t], logp_out=self.logp_traj[t])
             else:
-                obs_n = self.rms.normalize(self.obs)
+                obs_n = self.rms.normalize(obs_t)
                 mean = _mlp_apply(self.policy, obs_n, self.nh_p)
                 eps = torch.randn(mean.shape, device=self.dev)          # default CUDA generator: graph-capture safe
                 act = mean + torch.exp(self.log_std) * eps
@@ -184,7 +194,7 @@ class PPOTrainer:
                 self.logp_traj[t].copy_(gaussian_logprob(mean, self.log_std, act))
             # the step writes the next observation and this step's reward / terminated / truncated where the trainer keeps them
             self.v_step.autoreset(self.state, act, keys, inplace=True,
-                                  out=(self.obs, self.r_traj[t], self.term_traj[t], self.trunc_traj[t]))
+                                  out=(obs_next, self.r_traj[t], self.term_traj[t], self.trunc_traj[t]))
 
     @torch.no_grad()
     def collect_rollout(self):
