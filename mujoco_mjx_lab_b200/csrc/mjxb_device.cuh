@@ -1241,8 +1241,9 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
           }
           float dinv;
           if (tree_ok || (phase != 1 && C.tree_chol_ok != 0)) {  // M and M + h*damping always follow the tree pattern; H does unless a row couples two limbs
-            chol_tree(S, lane, a, dinv);
-            x = chol_tree_solve(S, lane, a, dinv, (lane < NV) ? rhs : 0.0f);
+            float zf = (lane < NV) ? rhs : 0.0f;   // forward substitution fused into the factorisation
+            chol_tree(S, lane, a, dinv, zf);
+            x = chol_tree_solve(S, lane, a, dinv, zf);
             if (MJXB_FACTOR_REUSE && LS_EXACT && phase == 1) { dinv_keep[lane] = dinv; factor_valid = true; }
           } else {
             chol_rows(S, lane, a, dinv);
