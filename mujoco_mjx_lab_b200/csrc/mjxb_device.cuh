@@ -1224,14 +1224,22 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
             for (int j = 0; j < NV; j++) a[j] += (j == lane) ? hd : 0.0f;
           }
           if (phase == 1 && (LS_EXACT || C.solver == 2)) {  // Newton: H = M + J^T diag(D*active) J ; CG preconditions with M alone
-            for (int r = 0; r < nrow; r++) {
-              if (!(S.rJaref[r] < 0.0f)) continue;  // row inactive at the current iterate (warp-uniform)
-              const float w = S.rD[r] * S.J[r * NVP + (lane < NVP ? lane : 0)];
-              const float4* jr = reinterpret_cast<const float4*>(&S.J[r * NVP]);
+            // rows active at the current iterate, as a bit mask per strip of 32: the loop below then depends on no shared-memory
+            // load (row r+1's loads are issued under row r's FMAs) and inactive rows cost nothing
+#pragma unroll 1
+            for (int st = 0; st < NSTRIP; st++) {
+              const int rl = st * 32 + lane;
+              unsigned act = __ballot_sync(FULL, rl < nrow && S.rJaref[rl] < 0.0f);
+              while (act != 0u) {
+                const int r = st * 32 + __ffs(act) - 1;
+                act &= act - 1u;
+                const float w = S.rD[r] * S.J[r * NVP + (lane < NVP ? lane : 0)];
+                const float4* jr = reinterpret_cast<const float4*>(&S.J[r * NVP]);
 #pragma unroll
-              for (int g = 0; g < NVP / 4; g++) {
-                float4 jj = jr[g];
-                a[4 * g] += w * jj.x; a[4 * g + 1] += w * jj.y; a[4 * g + 2] += w * jj.z; a[4 * g + 3] += w * jj.w;
+                for (int g = 0; g < NVP / 4; g++) {
+                  float4 jj = jr[g];
+                  a[4 * g] += w * jj.x; a[4 * g + 1] += w * jj.y; a[4 * g + 2] += w * jj.z; a[4 * g + 3] += w * jj.w;
+                }
               }
             }
           }
