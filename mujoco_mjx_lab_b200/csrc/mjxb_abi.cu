@@ -483,6 +483,12 @@ int mjxb_model_dims(const mjxb_model* m, int32_t dims[8]) {
 
 size_t mjxb_model_scratch_bytes(const mjxb_model* m) { return m ? (3 * (size_t)m->ovf_cap + 4 + kResetPad) * sizeof(int) : 0; }
 
+#if MJXB_STAGE_CLOCK
+int mjxb_debug_stage_clock(int32_t* host_out, int32_t n_env) {  // profiling variant only (not part of include/mjxb.h)
+  return cudaMemcpyFromSymbol(host_out, ::g_stage_clock, sizeof(int) * 32 * (size_t)(n_env < 4096 ? n_env : 4096)) == cudaSuccess ? 0 : MJXB_ECUDA;
+}
+#endif
+
 int mjxb_launch_config(const mjxb_model* m, int32_t cfg[4]) {  // warps per CTA, dynamic smem bytes, SM count, sizeof(WarpS)
   if (!m || !cfg) return MJXB_EINVAL;
   cfg[0] = m->warps; cfg[1] = (int32_t)m->smem; cfg[2] = m->num_sms; cfg[3] = (int32_t)sizeof(WarpS<CAP_MAIN, MAXCC_MAIN>);

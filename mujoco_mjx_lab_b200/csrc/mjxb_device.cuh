@@ -427,6 +427,16 @@ __device__ __forceinline__ float chol_solve_rows(WS& S, int lane, const float (&
 struct LSPoint { float alpha, cost, d0, d1; };
 
 }  // namespace mjxb
+// Profiling aid (tools/stage_clock.py builds a variant with -DMJXB_STAGE_CLOCK=1): per-env clock() stamps at the stage boundaries
+#ifndef MJXB_STAGE_CLOCK
+#define MJXB_STAGE_CLOCK 0
+#endif
+#if MJXB_STAGE_CLOCK
+__device__ int g_stage_clock[4096 * 32];
+#define MJXB_STAMP(i) do { if (lane == 0 && valid && env < 4096) g_stage_clock[env * 32 + (i)] = (int)clock(); } while (0)
+#else
+#define MJXB_STAMP(i) do { } while (0)
+#endif
 #ifndef MJXB_FACTOR_REUSE
 #define MJXB_FACTOR_REUSE 1
 #endif
@@ -585,6 +595,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
       if (istep == 0 || mode == MODE_ENV_RESET) S.vec[VCTRL][lane] = ctrl;  // constant over the in-kernel steps
       __syncwarp();
 
+      MJXB_STAMP(0);
       // ---------------------------------------------------------------- kinematics: parallel prefix over the joint tree
       // Lane j holds the rigid transform of joint j relative to the frame before it (body offset folded into a body's first joint);
       // log2(depth) rounds of pointer jumping with shuffles compose it up the chain to the world frame after the joint. The joint
@@ -678,6 +689,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
         __syncwarp();
       }
 
+      MJXB_STAMP(1);
       // ---------------------------------------------------------------- geoms, sites, frames the env layer reads
       if (lane < C.ngeom) {
         const int b = C.geom_body[lane];
@@ -707,6 +719,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
         if (A.dbg.xquat && lane < nbody) for (int k = 0; k < 4; k++) A.dbg.xquat[((size_t)env * nbody + lane) * 4 + k] = S.a.xquat[lane][k];
       }
 
+      MJXB_STAMP(2);
       // ---------------------------------------------------------------- com_pos: subtree com of the single tree, cinert, cdof
       float com[3];
       {
@@ -773,6 +786,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
       }
       __syncwarp();
 
+      MJXB_STAMP(3);
       // ---------------------------------------------------------------- com_vel + cacc: two inclusive prefix sums over the dof tree
       // cvel[b] = sum of cdof_d*qvel_d over the dofs moving b; cdof_dot_d = (cvel before dof d) x cdof_d; cacc[b] = -g + sum cdof_dot_d*qvel_d
       // (mjx smooth.com_vel / rne forward pass; the free joint's angular dofs see the velocity after its three linear dofs only).
@@ -872,6 +886,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
       for (int i = lane; i < NV * NVP; i += 32) S.M[i] = 0.0f;
       __syncwarp();
 
+      MJXB_STAMP(4);
       // ---------------------------------------------------------------- crb mass matrix, bias, passive, actuation
       float qfs = 0.0f;  // qfrc_smooth
       if (lane < NV) {
@@ -909,6 +924,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
         for (int i = lane; i < NV * NV; i += 32) A.dbg.qM[(size_t)env * NV * NV + i] = S.M[(i / NV) * NVP + (i % NV)];
       }
 
+      MJXB_STAMP(5);
       // ---------------------------------------------------------------- collision: lane per geom pair, candidates compacted by ballot
       int ncc = 0;
       bool tree_ok = C.tree_chol_ok != 0;
@@ -999,6 +1015,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
       if (ncc > MAXCC) { overflow = true; ncc = MAXCC; }
       __syncwarp();
 
+      MJXB_STAMP(6);
       // ---------------------------------------------------------------- constraint rows: joint limits, tendon limits, contacts
       int nrow = 0;
       {
@@ -1152,6 +1169,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
       }
       if (A.lockstep > 0 && pass == 0) group_sync(warp, A.lockstep_group);  // all warps of the group enter the solver code together
 
+      MJXB_STAMP(7);
       // ---------------------------------------------------------------- solve: one factor/solve code instance drives
       //   phase 0: qacc_smooth = M^-1 qfrc_smooth         (mjx smooth.factor_m/solve_m)
       //   phase 1: Newton  Mgrad = (M + J^T D_act J)^-1 grad (mjx solver._update_gradient), repeated
@@ -1201,6 +1219,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
             phase = 2;
           }
         }
+        if (phase == 1 && niter == 0) MJXB_STAMP(16);
         // ---- assemble the rows of the system matrix in registers, factor, solve
         // Newton iterations whose active set did not change since the last factorisation (typically the final, polishing ones)
         // reuse that factor: H = M + J^T diag(D*active) J would be rebuilt bit for bit, so the solve reads the rows of R kept in S.L.
@@ -1250,8 +1269,11 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
           float dinv;
           if (tree_ok || (phase != 1 && C.tree_chol_ok != 0)) {  // M and M + h*damping always follow the tree pattern; H does unless a row couples two limbs
             float zf = (lane < NV) ? rhs : 0.0f;   // forward substitution fused into the factorisation
+            if (phase == 1 && niter == 0) MJXB_STAMP(17);
             chol_tree(S, lane, a, dinv, zf);
+            if (phase == 1 && niter == 0) MJXB_STAMP(18);
             x = chol_tree_solve(S, lane, a, dinv, zf);
+            if (phase == 1 && niter == 0) MJXB_STAMP(19);
             if (MJXB_FACTOR_REUSE && LS_EXACT && phase == 1) { dinv_keep[lane] = dinv; factor_valid = true; }
           } else {
             chol_rows(S, lane, a, dinv);
@@ -1292,6 +1314,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
           update_constraint();
           grad = Ma - qfs - qfc;
           phase = 1;
+          MJXB_STAMP(8);
           continue;
         }
         if (phase == 2) { qacc_int = x; break; }
@@ -1310,6 +1333,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
         {
           const float mv = matvec_M(S, lane, search);
           rows_times(S, lane, nrow, search, S.rjv);
+          if (niter == 0) MJXB_STAMP(20);
           const float qg0 = gauss;
           const float qg1 = warp_sum((lane < NV) ? search * Ma : 0.0f) - warp_sum((lane < NV) ? search * qfs : 0.0f);
           const float qg2 = 0.5f * warp_sum((lane < NV) ? search * mv : 0.0f);
@@ -1319,6 +1343,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
             // alpha_r = -Jaref_r / jv_r; MJX's bracketed Newton iteration (solver._linesearch) converges to the same point.
             // Lane r evaluates f'(alpha_r) over all rows (128-bit broadcast loads, no shuffles), two warp min/max reductions
             // bracket the root, and the root of the linear piece inside the bracket is taken in closed form.
+            if (niter == 0) MJXB_STAMP(24);
             float* rls = S.rforce;   // per-row D*jv, published for the sweep (rforce is rebuilt by update_constraint)
             float al[NSTRIP], gp[NSTRIP];
             bool ok[NSTRIP];
@@ -1335,6 +1360,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
               }
             }
             __syncwarp();
+            if (niter == 0) MJXB_STAMP(25);
             for (int r2 = 0; r2 < nrow; r2++) {
               const float ja = S.rJaref[r2], jv = S.rjv[r2], dj = rls[r2];
 #pragma unroll
@@ -1343,6 +1369,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
                 gp[st] += (x < 0.0f) ? dj * x : 0.0f;
               }
             }
+            if (niter == 0) MJXB_STAMP(26);
             unsigned lo_b = 0u, hi_b = 0x7f800000u;  // positive floats order like their bit patterns
 #pragma unroll
             for (int st = 0; st < NSTRIP; st++) {
@@ -1354,6 +1381,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
             hi_b = __reduce_min_sync(FULL, hi_b);
             const float a_lo = __uint_as_float(lo_b), a_hi = __uint_as_float(hi_b);
             const float a_mid = (hi_b == 0x7f800000u) ? (2.0f * a_lo + 1.0f) : 0.5f * (a_lo + a_hi);
+            if (niter == 0) MJXB_STAMP(27);
             float sa = 0.0f, sb = 0.0f, sc = 0.0f;  // quadratic piece on (a_lo, a_hi): f = C + alpha A + alpha^2 B
             for (int r = lane; r < nrow; r += 32) {
               const float ja = S.rJaref[r], jv = S.rjv[r], dj = rls[r];
@@ -1362,6 +1390,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
               sb += on ? dj * jv : 0.0f;
               sc += on ? S.rD[r] * ja * ja : 0.0f;
             }
+            if (niter == 0) MJXB_STAMP(28);
             const float Aq = qg1 + warp_sum(sa), Bq = qg2 + 0.5f * warp_sum(sb), Cq = qg0 + 0.5f * warp_sum(sc);
             float a_star = (Bq > 0.0f) ? -Aq / (2.0f * Bq) : 0.0f;
             a_star = fminf(fmaxf(a_star, a_lo), a_hi);
@@ -1427,6 +1456,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
           const bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
           alpha_step = improved ? (lo.cost < hi.cost ? lo.alpha : hi.alpha) : 0.0f;
           }
+          if (niter == 0) MJXB_STAMP(21);
           if (alpha_step != 0.0f) {
             qacc += search * alpha_step;
             Ma += mv * alpha_step;
@@ -1440,8 +1470,10 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
           }
           __syncwarp();
         }
+        if (niter == 0) MJXB_STAMP(22);
         update_constraint();
         grad = Ma - qfs - qfc;
+        if (niter == 0) MJXB_STAMP(23);
         niter++;
       }  // factor/solve loop
 
@@ -1460,6 +1492,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
         }
       }
 
+      MJXB_STAMP(9);
       // ---------------------------------------------------------------- touch sensors (mjx sensor.sensor_acc / engine_sensor.c mjSENS_TOUCH)
       {
 #pragma unroll 1
@@ -1496,6 +1529,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
       const float qacc_solver = qacc;  // qacc_warmstart <- solver qacc (mjx solver.solve tail)
       if (!(fabsf(qacc_solver) < 3.0e38f)) status |= MJXB_STATUS_NAN;
 
+      MJXB_STAMP(10);
       // ---------------------------------------------------------------- integrate (mjx forward._advance)
       if (integrate_pass) {
         q = S.vec[VQPOS][lane];
@@ -1528,6 +1562,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
       ws = qacc_solver;
       if (!(fabsf(q) < 3.0e38f) || !(fabsf(v) < 3.0e38f)) status |= MJXB_STATUS_NAN;
 
+      MJXB_STAMP(11);
       // ---------------------------------------------------------------- env layer (src/envs.py) on the forward-pass frames
       if (mode == MODE_ENV_STEP || mode == MODE_ENV_RESET) {
         __syncwarp();
@@ -1649,6 +1684,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
       continue;
     }
 
+      MJXB_STAMP(12);
     // ------------------------------------------------------------------ store
     if (deferred) {  // step results now, state / obs / aux from the reset phase
       if (lane == 0) {
@@ -1676,6 +1712,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
       }
     }
     if (A.status && lane == 0) A.status[env] = reset_phase ? (A.status[env] | status) : status;
+    MJXB_STAMP(13);
     __syncwarp();
   }
   if (consuming) {  // last CTA out resets the consumed list's counters for the next step
