@@ -1175,7 +1175,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
       //   phase 1: Newton  Mgrad = (M + J^T D_act J)^-1 grad (mjx solver._update_gradient), repeated
       //   phase 2: qacc'   = (M + h*damping)^-1 (qfrc_smooth + qfrc_constraint)   (mjx forward.implicit / euler)
       float qas = 0.0f, qacc = 0.0f, Ma = 0.0f, qfc = 0.0f, grad = 0.0f, search = 0.0f;
-      float gauss = 0.0f, cost = 0.0f, prev_cost = 0.0f, prev_grad = 0.0f, prev_Mgrad = 0.0f;
+      float gauss = 0.0f, cost = 0.0f, prev_cost = 0.0f, prev_grad = 0.0f, prev_Mgrad = 0.0f, grad_sq = 0.0f;
       int niter = 0, phase = 0;
       bool factor_valid = false;           // S.L / dinv_keep hold the factor of H for the current active set (tree pattern only)
       float* dinv_keep = &S.gpos[0][0];    // geom frames are dead after the collision stage: 32 floats of 1/R_ii
@@ -1195,7 +1195,11 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
         }
         __syncwarp();
         qfc = rowsT_times(S, lane, nrow, S.rforce);
+        grad = Ma - qfs - qfc;
+        // three reductions side by side (the compiler interleaves the shuffle chains): gauss, cost, and the squared gradient norm
+        // that the next termination test needs -- taken here it costs no dependent round of its own
         gauss = 0.5f * warp_sum((lane < NV) ? (Ma - qfs) * (qacc - qas) : 0.0f);
+        grad_sq = warp_sum((lane < NV) ? grad * grad : 0.0f);
         prev_cost = cost;
         cost = 0.5f * warp_sum(cs) + gauss;
       };
@@ -1209,7 +1213,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
             done = niter >= 1;
           } else {
             const float improvement = (prev_cost - cost) * scale;
-            const float gradient = sqrtf(warp_sum((lane < NV) ? grad * grad : 0.0f)) * scale;
+            const float gradient = sqrtf(grad_sq) * scale;
             done = (niter >= C.iterations) || (improvement < C.tolerance) || (gradient < C.tolerance);
             if (niter >= C.iterations && !(improvement < C.tolerance) && !(gradient < C.tolerance)) status |= MJXB_STATUS_MAXITER;
           }
@@ -1312,7 +1316,6 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
           cost = __int_as_float(0x7f800000);  // Context.create: cost = inf, prev_cost = 0
           prev_cost = 0.0f;
           update_constraint();
-          grad = Ma - qfs - qfc;
           phase = 1;
           MJXB_STAMP(8);
           continue;
@@ -1472,7 +1475,6 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
         }
         if (niter == 0) MJXB_STAMP(22);
         update_constraint();
-        grad = Ma - qfs - qfc;
         if (niter == 0) MJXB_STAMP(23);
         niter++;
       }  // factor/solve loop

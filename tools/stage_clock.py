@@ -42,6 +42,10 @@ inner = ["H build (M load + active rows)", "factor + forward subst.", "backward 
          "apply step", "update_constraint + grad"]
 di = np.diff(out[:, 16:24].astype(np.int64), axis=1)
 ok = it >= 1
+dense = ok & ((out[:, 18] - out[:, 17]) <= 0)
+print(f"  envs on the dense-factorisation path (a candidate contact couples two limbs): {dense.sum()} of {ok.sum()} ({100.0 * dense.sum() / max(ok.sum(), 1):.2f} %)")
+print(f"  whole first iteration, tree path {np.median((out[ok & ~dense, 23] - out[ok & ~dense, 16])):.0f} cycles, dense path {np.median((out[dense, 23] - out[dense, 16])) if dense.any() else float('nan'):.0f} cycles")
+ok = ok & ~dense
 print("  first Newton iteration, stage latencies (cycles):")
 for i, nm in enumerate(inner):
     print(f"    {nm:34s} mean {di[ok, i].mean():7.0f}  p95 {np.percentile(di[ok, i], 95):7.0f}")
