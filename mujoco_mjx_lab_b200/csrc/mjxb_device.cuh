@@ -341,6 +341,39 @@ __device__ __forceinline__ float matvec_M(WS& S, int lane, float x) {
   }
   return acc;
 }
+// matvec_M and rows_times of the same x with one publication of x and the two 28-term dependent FMA chains of a lane (its row of M,
+// its row of J) interleaved -- same per-chain order, so the results are bit-identical to the separate calls
+template <class WS>
+__device__ __forceinline__ float matvec_M_and_rows(WS& S, int lane, int nrow, float x, float* out /* smem [CAP] */) {
+  __syncwarp();
+  S.vec[VX][lane] = (lane < NV) ? x : 0.0f;
+  __syncwarp();
+  const float4* xv = reinterpret_cast<const float4*>(&S.vec[VX][0]);
+  const float4* mrow = reinterpret_cast<const float4*>(&S.M[(lane < NV ? lane : 0) * NVP]);
+  const float4* jrow = reinterpret_cast<const float4*>(&S.J[(lane < nrow ? lane : 0) * NVP]);
+  float accm = 0.0f, accj = 0.0f;
+#pragma unroll
+  for (int g = 0; g < NVP / 4; g++) {
+    const float4 xx = xv[g], m = mrow[g], j = jrow[g];
+    accm += m.x * xx.x; accj += j.x * xx.x;
+    accm += m.y * xx.y; accj += j.y * xx.y;
+    accm += m.z * xx.z; accj += j.z * xx.z;
+    accm += m.w * xx.w; accj += j.w * xx.w;
+  }
+  if (lane < nrow) out[lane] = accj;
+  for (int r = 32 + lane; r < nrow; r += 32) {   // further strips (capacity tiers above 32 rows)
+    const float4* row = reinterpret_cast<const float4*>(&S.J[r * NVP]);
+    float acc = 0.0f;
+#pragma unroll
+    for (int g = 0; g < NVP / 4; g++) {
+      float4 m = row[g], xx = xv[g];
+      acc += m.x * xx.x; acc += m.y * xx.y; acc += m.z * xx.z; acc += m.w * xx.w;
+    }
+    out[r] = acc;
+  }
+  __syncwarp();
+  return (lane < NV) ? accm : 0.0f;
+}
 // out[r] = sum_d J[r][d] x_d for all rows (lane-per-row strips); x published through vec[VX]
 template <class WS>
 __device__ __forceinline__ void rows_times(WS& S, int lane, int nrow, float x, float* out /* smem [CAP] */) {
@@ -1290,8 +1323,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
           if (DBG && A.dbg.qacc_smooth && lane < NV) A.dbg.qacc_smooth[(size_t)env * NV + lane] = qas;
           // warm start (mjx solver.solve): cheaper of qacc_warmstart and qacc_smooth
           const float w0 = S.vec[VX][lane];  // qacc_warmstart (parked at the top of the pass)
-          float Ma_w = matvec_M(S, lane, w0);
-          rows_times(S, lane, nrow, w0, S.rjv);  // J*warm
+          float Ma_w = matvec_M_and_rows(S, lane, nrow, w0, S.rjv);  // M*warm, J*warm
           float cs = 0.0f;
           for (int r = lane; r < nrow; r += 32) {
             float ja = S.rjv[r] - S.raref[r];
@@ -1299,8 +1331,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
             cs += ja < 0.0f ? S.rD[r] * ja * ja : 0.0f;
           }
           float cost_w = 0.5f * warp_sum(cs) + 0.5f * warp_sum((lane < NV) ? (Ma_w - qfs) * (w0 - qas) : 0.0f);
-          float Ma_s = matvec_M(S, lane, qas);
-          rows_times(S, lane, nrow, qas, S.rJaref);
+          float Ma_s = matvec_M_and_rows(S, lane, nrow, qas, S.rJaref);
           cs = 0.0f;
           for (int r = lane; r < nrow; r += 32) {
             float ja = S.rJaref[r] - S.raref[r];
@@ -1334,8 +1365,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
         if (!LS_EXACT) { prev_grad = grad; prev_Mgrad = x; }
         // ---- line search along `search`: minimise f(alpha) = gauss-quadratic + sum_r [Jaref_r + alpha jv_r < 0] D_r (Jaref_r + alpha jv_r)^2 / 2
         {
-          const float mv = matvec_M(S, lane, search);
-          rows_times(S, lane, nrow, search, S.rjv);
+          const float mv = matvec_M_and_rows(S, lane, nrow, search, S.rjv);
           if (niter == 0) MJXB_STAMP(20);
           const float qg0 = gauss;
           const float qg1 = warp_sum((lane < NV) ? search * Ma : 0.0f) - warp_sum((lane < NV) ? search * qfs : 0.0f);
