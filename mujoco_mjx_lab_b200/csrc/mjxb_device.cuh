@@ -485,6 +485,9 @@ __device__ __forceinline__ void group_sync(int warp, int g) {
   asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(cnt) : "memory");
 }
 
+// lane-per-row loop over the candidate rows with a compile-time trip bound (NSTRIP = ceil(CAP / 32), 1 for the main tier): a plain
+// `for (r = lane; r < nrow; r += 32)` is unrolled eightfold by the compiler with branchy prologues although it runs exactly once
+#define MJXB_FOR_ROW_STRIPS(r) _Pragma("unroll") for (int r = lane, strip_ = 0; strip_ < NSTRIP && r < nrow; strip_++, r += 32)
 // ------------------------------------------------------------------------------------------- the kernel
 // SINGLE: one step per launch and resets always deferred -> no loop-carried per-env registers across the step / pass loops.
 template <bool DBG, int CAP, int MAXCC, int MAXW, bool LS_EXACT, bool SINGLE = false>
@@ -1154,7 +1157,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
         __syncwarp();
         // per-row impedance / reference acceleration (lane per row)
         const float4* qv4 = reinterpret_cast<const float4*>(&S.vec[VQVEL][0]);
-        for (int rr = lane; rr < nrow; rr += 32) {
+        MJXB_FOR_ROW_STRIPS(rr) {
           const int info = S.rinfo[rr], kind = info & 3, idx = (info >> 2) & 0xff;
           const float rpos = S.rJaref[rr];
           float invw, solref[2], solimp[5];
@@ -1220,7 +1223,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
       // update_constraint (mjx solver._update_constraint) on the current Jaref/Ma/qacc
       auto update_constraint = [&]() {
         float cs = 0.0f;
-        for (int r = lane; r < nrow; r += 32) {
+        MJXB_FOR_ROW_STRIPS(r) {
           const float ja = S.rJaref[r], D = S.rD[r];
           const bool active = ja < 0.0f;
           S.rforce[r] = active ? -D * ja : 0.0f;
@@ -1325,7 +1328,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
           const float w0 = S.vec[VX][lane];  // qacc_warmstart (parked at the top of the pass)
           float Ma_w = matvec_M_and_rows(S, lane, nrow, w0, S.rjv);  // M*warm, J*warm
           float cs = 0.0f;
-          for (int r = lane; r < nrow; r += 32) {
+          MJXB_FOR_ROW_STRIPS(r) {
             float ja = S.rjv[r] - S.raref[r];
             S.rjv[r] = ja;
             cs += ja < 0.0f ? S.rD[r] * ja * ja : 0.0f;
@@ -1333,7 +1336,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
           float cost_w = 0.5f * warp_sum(cs) + 0.5f * warp_sum((lane < NV) ? (Ma_w - qfs) * (w0 - qas) : 0.0f);
           float Ma_s = matvec_M_and_rows(S, lane, nrow, qas, S.rJaref);
           cs = 0.0f;
-          for (int r = lane; r < nrow; r += 32) {
+          MJXB_FOR_ROW_STRIPS(r) {
             float ja = S.rJaref[r] - S.raref[r];
             S.rJaref[r] = ja;
             cs += ja < 0.0f ? S.rD[r] * ja * ja : 0.0f;
@@ -1342,7 +1345,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
           const bool use_warm = cost_w < cost_s;
           qacc = use_warm ? w0 : qas;
           Ma = use_warm ? Ma_w : Ma_s;
-          if (use_warm) for (int r = lane; r < nrow; r += 32) S.rJaref[r] = S.rjv[r];
+          if (use_warm) MJXB_FOR_ROW_STRIPS(r) S.rJaref[r] = S.rjv[r];
           __syncwarp();
           cost = __int_as_float(0x7f800000);  // Context.create: cost = inf, prev_cost = 0
           prev_cost = 0.0f;
@@ -1416,7 +1419,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
             const float a_mid = (hi_b == 0x7f800000u) ? (2.0f * a_lo + 1.0f) : 0.5f * (a_lo + a_hi);
             if (niter == 0) MJXB_STAMP(27);
             float sa = 0.0f, sb = 0.0f, sc = 0.0f;  // quadratic piece on (a_lo, a_hi): f = C + alpha A + alpha^2 B
-            for (int r = lane; r < nrow; r += 32) {
+            MJXB_FOR_ROW_STRIPS(r) {
               const float ja = S.rJaref[r], jv = S.rjv[r], dj = rls[r];
               const bool on = fmaf(a_mid, jv, ja) < 0.0f;
               sa += on ? dj * ja : 0.0f;
@@ -1494,7 +1497,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
             qacc += search * alpha_step;
             Ma += mv * alpha_step;
             bool flip = false;
-            for (int r = lane; r < nrow; r += 32) {
+            MJXB_FOR_ROW_STRIPS(r) {
               const float ja0 = S.rJaref[r], ja1 = ja0 + S.rjv[r] * alpha_step;
               flip |= (ja0 < 0.0f) != (ja1 < 0.0f);
               S.rJaref[r] = ja1;
@@ -1517,7 +1520,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
           if (A.dbg.qfrc_constraint) A.dbg.qfrc_constraint[(size_t)env * NV + lane] = qfc;
         }
         if (A.dbg.solver_niter && lane == 0) A.dbg.solver_niter[env] = niter;
-        for (int r = lane; r < nrow; r += 32) {
+        MJXB_FOR_ROW_STRIPS(r) {
           const int efc_row = S.rinfo[r] >> 16;
           if (A.dbg.efc_force) A.dbg.efc_force[(size_t)env * C.nefc + efc_row] = S.rforce[r];
           if (A.dbg.efc_active) A.dbg.efc_active[(size_t)env * C.nefc + efc_row] = 1 | (S.rJaref[r] < 0.0f ? 2 : 0);
