@@ -1085,7 +1085,8 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
         nrow += __popc(mk);
         // contacts: exclusive scan of rows per candidate, 32 candidates per strip (the big tier holds up to 176)
         int total = 0;
-        for (int cb = 0; cb < ncc; cb += 32) {
+#pragma unroll
+        for (int cb = 0, cstrip_ = 0; cstrip_ < (MAXCC + 31) / 32 && cb < ncc; cstrip_++, cb += 32) {
           const int c = cb + lane;
           int nr = 0;
           if (c < ncc) nr = ((S.cc_pair[c] >> 20) > 1) ? 4 : 1;
@@ -1534,7 +1535,8 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
         for (int s = 0; s < C.nsensor; s++) {
           float contrib = 0.0f;
           const int site = C.sensor_site[s], sb = C.site_body[site];
-          for (int c = lane; c < ncc; c += 32) {
+#pragma unroll
+          for (int c = lane, cstrip_ = 0; cstrip_ < (MAXCC + 31) / 32 && c < ncc; cstrip_++, c += 32) {
             const int pr = S.cc_pair[c], p = pr & 0xffff, rb = S.cc_row[c];
             const uint32_t w0 = C.pair_w0[p];
             const int b1 = C.geom_body[w0 & 0xff], b2 = C.geom_body[(w0 >> 8) & 0xff];
