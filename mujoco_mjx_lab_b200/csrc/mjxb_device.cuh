@@ -470,9 +470,6 @@ __device__ int g_stage_clock[4096 * 32];
 #else
 #define MJXB_STAMP(i) do { } while (0)
 #endif
-#ifndef MJXB_OPT_SWEEP2   // experiment: two rows per trip in the line-search derivative sweep (off until measured)
-#define MJXB_OPT_SWEEP2 0
-#endif
 #ifndef MJXB_FACTOR_REUSE
 #define MJXB_FACTOR_REUSE 1
 #endif
@@ -1401,27 +1398,12 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
             }
             __syncwarp();
             if (niter == 0) MJXB_STAMP(25);
-            {  // two rows per trip, loads first: the second row's broadcast loads are in flight under the first row's arithmetic
-              int r2 = 0;
-#pragma unroll 1
-              for (; MJXB_OPT_SWEEP2 && r2 + 1 < nrow; r2 += 2) {
-                const float ja = S.rJaref[r2], jv = S.rjv[r2], dj = rls[r2];
-                const float jb = S.rJaref[r2 + 1], jw = S.rjv[r2 + 1], dk = rls[r2 + 1];
+            for (int r2 = 0; r2 < nrow; r2++) {
+              const float ja = S.rJaref[r2], jv = S.rjv[r2], dj = rls[r2];
 #pragma unroll
-                for (int st = 0; st < NSTRIP; st++) {
-                  const float x = fmaf(al[st], jv, ja);
-                  gp[st] += (x < 0.0f) ? dj * x : 0.0f;
-                  const float y = fmaf(al[st], jw, jb);
-                  gp[st] += (y < 0.0f) ? dk * y : 0.0f;
-                }
-              }
-              for (; r2 < nrow; r2++) {
-                const float ja = S.rJaref[r2], jv = S.rjv[r2], dj = rls[r2];
-#pragma unroll
-                for (int st = 0; st < NSTRIP; st++) {
-                  const float x = fmaf(al[st], jv, ja);
-                  gp[st] += (x < 0.0f) ? dj * x : 0.0f;
-                }
+              for (int st = 0; st < NSTRIP; st++) {
+                const float x = fmaf(al[st], jv, ja);
+                gp[st] += (x < 0.0f) ? dj * x : 0.0f;
               }
             }
             if (niter == 0) MJXB_STAMP(26);
