@@ -964,9 +964,38 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
       // ---------------------------------------------------------------- collision: lane per geom pair, candidates compacted by ballot
       int ncc = 0;
       bool tree_ok = C.tree_chol_ok != 0;
+      // Broad phase: a pair whose bounding spheres (capsule: half length + radius around the geom centre; plane: centre height) are
+      // apart cannot penetrate, so it cannot become a candidate (dist < 0). The survivors (typically 10-20 of 108) are compacted in
+      // pair order -- the candidate order, hence every later rounding, is unchanged -- and the narrow phase below runs over one or two
+      // strips of 32 instead of four. Debug builds keep every pair (they report all distances).
+      int* pot_list = reinterpret_cast<int*>(&S.J[0]);   // J is not written before the constraint stage
+      int npot = 0;
       for (int base = 0; base < C.npair; base += 32) {
         const int p = base + lane;
-        const bool valid = p < C.npair;
+        bool pot = false;
+        if (p < C.npair) {
+          pot = true;
+          if (!DBG) {
+            const uint32_t w0 = C.pair_w0[p];
+            const int g1 = w0 & 0xff, g2 = (w0 >> 8) & 0xff, kd = (w0 >> 16) & 0xff;
+            const float dx = S.gpos[g2][0] - S.gpos[g1][0], dy = S.gpos[g2][1] - S.gpos[g1][1], dz = S.gpos[g2][2] - S.gpos[g1][2];
+            const float e2 = C.geom_rad[g2] + C.geom_half[g2];
+            if (kd == PAIR_PLANE_CAPSULE || kd == PAIR_PLANE_SPHERE) {
+              pot = dx * S.gaxis[g1][0] + dy * S.gaxis[g1][1] + dz * S.gaxis[g1][2] - e2 <= 1e-5f;
+            } else {
+              const float reach = C.geom_rad[g1] + C.geom_half[g1] + e2;
+              pot = dx * dx + dy * dy + dz * dz <= reach * reach * 1.0001f + 1e-6f;
+            }
+          }
+        }
+        const unsigned mk = __ballot_sync(FULL, pot);
+        if (pot) pot_list[npot + __popc(mk & lt_mask)] = p;
+        npot += __popc(mk);
+      }
+      __syncwarp();
+      for (int base = 0; base < npot; base += 32) {
+        const bool valid = base + lane < npot;
+        const int p = valid ? pot_list[base + lane] : 0;
         float dist[2] = {1.0f, 1.0f}, cpos[2][3] = {{0, 0, 0}, {0, 0, 0}}, n[3] = {0, 0, 1}, t1[3] = {0, 0, 0}, t2[3] = {0, 0, 0};
         int kind = -1, condim = 1;
         bool cross_branch = false;
