@@ -1126,7 +1126,10 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
             if (lane >= o) scan += t;
           }
           const int rbase = nrow + total + scan - nr;
-          if (c < ncc) S.cc_row[c] = (rbase + nr <= CAP) ? rbase : -1;
+          if (c < ncc) {
+            S.cc_row[c] = (rbase + nr <= CAP) ? rbase : -1;
+            S.rforce[c] = pair_param[S.cc_pair[c] & 0xffff].mu;   // friction of every candidate fetched in one round (global memory);
+          }                                                        // rforce is free until the solver starts
           total += __shfl_sync(FULL, scan, 31);
         }
         if (nrow + total > CAP) overflow = true;
@@ -1171,7 +1174,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
             if (!c3) {
               S.J[rb * NVP + lane] = jn;
             } else {
-              const float mu = pair_param[p].mu;
+              const float mu = S.rforce[c];
               float j1 = dot3(S.cc_t1[c], jc) * mu, j2 = dot3(S.cc_t2[c], jc) * mu;
               S.J[(rb + 0) * NVP + lane] = jn + j1;
               S.J[(rb + 1) * NVP + lane] = jn - j1;
