@@ -328,9 +328,9 @@ int launch(const mjxb_model* mc, const StepArgs& args_in, bool dbg, cudaStream_t
   int* listB = ovf + 4 + cap;
   args.in_count = nullptr; args.in_list = nullptr; args.in_done = nullptr; args.out_count = ovf; args.out_list = listA;
   args.reset_list = (getenv("MJXB_INLINE_RESET") != nullptr) ? nullptr : ovf + 4 + 2 * (size_t)cap;
-  // 3 (default): CTA barriers at the round top, the solver entry and every factor/solve round; 1: round top + solver entry/exit only;
-  // 0: none (profiling aid)
-  { const char* e = getenv("MJXB_LOCKSTEP"); args.lockstep = e ? atoi(e) : 3; }
+  // 1 (default): CTA barriers at the round top and at the solver entry / exit; 3: additionally at every factor/solve round (was the
+  // better choice before the solver's dependent chains were shortened: 35.2 M against 36.4 M now); 0: none (profiling aid)
+  { const char* e = getenv("MJXB_LOCKSTEP"); args.lockstep = e ? atoi(e) : 1; }
   { const char* e = getenv("MJXB_LOCKSTEP_GROUP"); args.lockstep_group = e ? atoi(e) : 0; }
   // small batches: spread the envs over every SM (fewer warps per CTA run faster than 16 sharing one SM's issue slots)
   int warps = m->warps;
