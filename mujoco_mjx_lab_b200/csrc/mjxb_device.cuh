@@ -374,6 +374,43 @@ __device__ __forceinline__ float matvec_M_and_rows(WS& S, int lane, int nrow, fl
   __syncwarp();
   return (lane < NV) ? accm : 0.0f;
 }
+// the same for two vectors at once (warm-start selection): M and J rows are loaded once, four dependent chains interleave
+template <class WS>
+__device__ __forceinline__ void matvec_M_and_rows2(WS& S, int lane, int nrow, float x1, float x2, float* out1, float* out2, float& m1,
+                                                   float& m2) {
+  __syncwarp();
+  S.vec[VX][lane] = (lane < NV) ? x1 : 0.0f;
+  S.vec[VTMP][lane] = (lane < NV) ? x2 : 0.0f;
+  __syncwarp();
+  const float4* xv = reinterpret_cast<const float4*>(&S.vec[VX][0]);
+  const float4* yv = reinterpret_cast<const float4*>(&S.vec[VTMP][0]);
+  const float4* mrow = reinterpret_cast<const float4*>(&S.M[(lane < NV ? lane : 0) * NVP]);
+  float am1 = 0.0f, am2 = 0.0f;
+#pragma unroll
+  for (int g = 0; g < NVP / 4; g++) {
+    const float4 xx = xv[g], yy = yv[g], m = mrow[g];
+    am1 += m.x * xx.x; am2 += m.x * yy.x;
+    am1 += m.y * xx.y; am2 += m.y * yy.y;
+    am1 += m.z * xx.z; am2 += m.z * yy.z;
+    am1 += m.w * xx.w; am2 += m.w * yy.w;
+  }
+  for (int r = lane; r < nrow; r += 32) {
+    const float4* row = reinterpret_cast<const float4*>(&S.J[r * NVP]);
+    float a1 = 0.0f, a2 = 0.0f;
+#pragma unroll
+    for (int g = 0; g < NVP / 4; g++) {
+      const float4 j = row[g], xx = xv[g], yy = yv[g];
+      a1 += j.x * xx.x; a2 += j.x * yy.x;
+      a1 += j.y * xx.y; a2 += j.y * yy.y;
+      a1 += j.z * xx.z; a2 += j.z * yy.z;
+      a1 += j.w * xx.w; a2 += j.w * yy.w;
+    }
+    out1[r] = a1; out2[r] = a2;
+  }
+  __syncwarp();
+  m1 = (lane < NV) ? am1 : 0.0f;
+  m2 = (lane < NV) ? am2 : 0.0f;
+}
 // out[r] = sum_d J[r][d] x_d for all rows (lane-per-row strips); x published through vec[VX]
 template <class WS>
 __device__ __forceinline__ void rows_times(WS& S, int lane, int nrow, float x, float* out /* smem [CAP] */) {
@@ -469,6 +506,9 @@ __device__ int g_stage_clock[4096 * 32];
 #define MJXB_STAMP(i) do { if (lane == 0 && valid && env < 4096) g_stage_clock[env * 32 + (i)] = (int)clock(); } while (0)
 #else
 #define MJXB_STAMP(i) do { } while (0)
+#endif
+#ifndef MJXB_WARM2   // warm-start candidates evaluated side by side (enabled once measured)
+#define MJXB_WARM2 0
 #endif
 #ifndef MJXB_FACTOR_REUSE
 #define MJXB_FACTOR_REUSE 1
@@ -1355,10 +1395,28 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
         }
 
         if (phase == 0) {
+          MJXB_STAMP(14);
           qas = x;
           if (DBG && A.dbg.qacc_smooth && lane < NV) A.dbg.qacc_smooth[(size_t)env * NV + lane] = qas;
           // warm start (mjx solver.solve): cheaper of qacc_warmstart and qacc_smooth
           const float w0 = S.vec[VX][lane];  // qacc_warmstart (parked at the top of the pass)
+#if MJXB_WARM2
+          // both candidates (qacc_warmstart, qacc_smooth) are evaluated side by side: one pass over M and J, one loop over the rows,
+          // four reductions next to each other (each sum keeps its own order: bit-identical to evaluating them one after the other)
+          float Ma_w, Ma_s;
+          matvec_M_and_rows2(S, lane, nrow, w0, qas, S.rjv, S.rJaref, Ma_w, Ma_s);
+          float cs = 0.0f, cs2 = 0.0f;
+          MJXB_FOR_ROW_STRIPS(r) {
+            const float ar = S.raref[r], D = S.rD[r];
+            const float ja = S.rjv[r] - ar, jb = S.rJaref[r] - ar;
+            S.rjv[r] = ja;
+            S.rJaref[r] = jb;
+            cs += ja < 0.0f ? D * ja * ja : 0.0f;
+            cs2 += jb < 0.0f ? D * jb * jb : 0.0f;
+          }
+          const float cost_w = 0.5f * warp_sum(cs) + 0.5f * warp_sum((lane < NV) ? (Ma_w - qfs) * (w0 - qas) : 0.0f);
+          const float cost_s = 0.5f * warp_sum(cs2) + 0.5f * warp_sum((lane < NV) ? (Ma_s - qfs) * (qas - qas) : 0.0f);
+#else
           float Ma_w = matvec_M_and_rows(S, lane, nrow, w0, S.rjv);  // M*warm, J*warm
           float cs = 0.0f;
           MJXB_FOR_ROW_STRIPS(r) {
@@ -1375,11 +1433,13 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
             cs += ja < 0.0f ? S.rD[r] * ja * ja : 0.0f;
           }
           float cost_s = 0.5f * warp_sum(cs) + 0.5f * warp_sum((lane < NV) ? (Ma_s - qfs) * (qas - qas) : 0.0f);
+#endif
           const bool use_warm = cost_w < cost_s;
           qacc = use_warm ? w0 : qas;
           Ma = use_warm ? Ma_w : Ma_s;
           if (use_warm) MJXB_FOR_ROW_STRIPS(r) S.rJaref[r] = S.rjv[r];
           __syncwarp();
+          MJXB_STAMP(15);
           cost = __int_as_float(0x7f800000);  // Context.create: cost = inf, prev_cost = 0
           prev_cost = 0.0f;
           update_constraint();

@@ -34,6 +34,8 @@ tot = (out[:, 13] - out[:, 0]).astype(np.int64)
 print(f"n={n}: total cycles/env-step mean {tot.mean():.0f} (max {tot.max()}), mean newton iters {niter[:m].mean():.2f}")
 for i, nm in enumerate(names[1:]):
     print(f"  {nm:22s} mean {dt[:, i].mean():8.0f}  p95 {np.percentile(dt[:, i], 95):8.0f}  ({100 * dt[:, i].mean() / tot.mean():4.1f} %)")
+print(f"  inside 'M^-1 + warm start': entry barrier + M factor/solve {np.median(out[:, 14] - out[:, 7]):.0f}, warm-start evaluation {np.median(out[:, 15] - out[:, 14]):.0f}, "
+      f"first update_constraint {np.median(out[:, 8] - out[:, 15]):.0f} (medians)")
 it = niter[:m]
 for k in sorted(set(it.tolist())):
     sel = it == k
