@@ -507,9 +507,6 @@ __device__ int g_stage_clock[4096 * 32];
 #else
 #define MJXB_STAMP(i) do { } while (0)
 #endif
-#ifndef MJXB_WARM2   // warm-start candidates evaluated side by side (enabled once measured)
-#define MJXB_WARM2 0
-#endif
 #ifndef MJXB_FACTOR_REUSE
 #define MJXB_FACTOR_REUSE 1
 #endif
@@ -1400,7 +1397,6 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
           if (DBG && A.dbg.qacc_smooth && lane < NV) A.dbg.qacc_smooth[(size_t)env * NV + lane] = qas;
           // warm start (mjx solver.solve): cheaper of qacc_warmstart and qacc_smooth
           const float w0 = S.vec[VX][lane];  // qacc_warmstart (parked at the top of the pass)
-#if MJXB_WARM2
           // both candidates (qacc_warmstart, qacc_smooth) are evaluated side by side: one pass over M and J, one loop over the rows,
           // four reductions next to each other (each sum keeps its own order: bit-identical to evaluating them one after the other)
           float Ma_w, Ma_s;
@@ -1416,24 +1412,6 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
           }
           const float cost_w = 0.5f * warp_sum(cs) + 0.5f * warp_sum((lane < NV) ? (Ma_w - qfs) * (w0 - qas) : 0.0f);
           const float cost_s = 0.5f * warp_sum(cs2) + 0.5f * warp_sum((lane < NV) ? (Ma_s - qfs) * (qas - qas) : 0.0f);
-#else
-          float Ma_w = matvec_M_and_rows(S, lane, nrow, w0, S.rjv);  // M*warm, J*warm
-          float cs = 0.0f;
-          MJXB_FOR_ROW_STRIPS(r) {
-            float ja = S.rjv[r] - S.raref[r];
-            S.rjv[r] = ja;
-            cs += ja < 0.0f ? S.rD[r] * ja * ja : 0.0f;
-          }
-          float cost_w = 0.5f * warp_sum(cs) + 0.5f * warp_sum((lane < NV) ? (Ma_w - qfs) * (w0 - qas) : 0.0f);
-          float Ma_s = matvec_M_and_rows(S, lane, nrow, qas, S.rJaref);
-          cs = 0.0f;
-          MJXB_FOR_ROW_STRIPS(r) {
-            float ja = S.rJaref[r] - S.raref[r];
-            S.rJaref[r] = ja;
-            cs += ja < 0.0f ? S.rD[r] * ja * ja : 0.0f;
-          }
-          float cost_s = 0.5f * warp_sum(cs) + 0.5f * warp_sum((lane < NV) ? (Ma_s - qfs) * (qas - qas) : 0.0f);
-#endif
           const bool use_warm = cost_w < cost_s;
           qacc = use_warm ? w0 : qas;
           Ma = use_warm ? Ma_w : Ma_s;
