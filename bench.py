@@ -85,6 +85,12 @@ def cpu_reference_run(n_env: int, steps: int, warmup: int, seed: int = 42):
     O.build()
     model = helpers.load()
     orc = helpers.make_oracle(model, helpers.env_config())
+    # every host core this process may use, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1 to its workers)
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncpu = os.cpu_count() or 1
+    orc.nthreads = ncpu
     rng = np.random.default_rng(seed)
     st, _ = orc.env_reset(helpers.ppo_keys(seed, n_env))
     for t in range(warmup):
@@ -93,7 +99,7 @@ def cpu_reference_run(n_env: int, steps: int, warmup: int, seed: int = 42):
     for t in range(steps):
         st, *_ = orc.env_step(st, np.clip(rng.normal(size=(n_env, 21)), -1, 1), reset_keys=helpers.ppo_keys(2000 + t, n_env))
     dt = time.perf_counter() - t0
-    return n_env * steps / dt, dt, O.max_threads()
+    return n_env * steps / dt, dt, ncpu
 
 
 def main():
