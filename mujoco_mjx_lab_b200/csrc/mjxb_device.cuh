@@ -25,7 +25,9 @@ constexpr int NVP = 28;   // row stride (floats) of M and J: 16-byte aligned row
 #ifndef MJXB_CAP_MAIN
 #define MJXB_CAP_MAIN 32
 #define MJXB_MAXCC_MAIN 16
+#ifndef MJXB_WARPS_MAIN
 #define MJXB_WARPS_MAIN 16
+#endif
 #endif
 constexpr int CAP_MAIN = MJXB_CAP_MAIN, MAXCC_MAIN = MJXB_MAXCC_MAIN, WARPS_MAIN = MJXB_WARPS_MAIN;
 constexpr int CAP_MID = 64, MAXCC_MID = 24, WARPS_MID = 10;
