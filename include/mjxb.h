@@ -13,11 +13,15 @@
  *   - every array argument of the *device* entry points is a CUDA device pointer owned by the caller,
  *     row-major [n_env, k] float32 ("structure of arrays": one array per state field);
  *     all work is enqueued on the caller's stream (`stream` is a cudaStream_t passed as void*);
- *     no allocation, no host synchronisation inside reset/step.
+ *     no host synchronisation inside reset/step. The only allocation is the per-stream launch scratch (overflow lists, 12 B / env),
+ *     made the first time a stream launches a batch larger than it has seen; mjxb_model_reserve(m, n_env, stream) makes it
+ *     ahead of time -- mandatory before capturing the stream into a CUDA graph. A scratch buffer is never freed or moved before
+ *     mjxb_model_destroy, so captured graphs stay valid.
  *   - the *_host entry points take host pointers and do H2D -> kernel -> D2H themselves (synchronous).
  *   - return value: 0 = ok, negative = MJXB_E* (argument / CUDA errors, reported synchronously).
  *     Numerical trouble is reported asynchronously per env through `status` (bit flags below).
- *   - mjxb_model is immutable after create; one model per device; thread-safe for distinct streams.
+ *   - the model constants are immutable after create; one model per device. Launches on distinct streams use distinct scratch
+ *     and may run concurrently from different threads; launches on ONE stream are ordered by the stream.
  */
 #ifndef MJXB_H_
 #define MJXB_H_
@@ -106,10 +110,23 @@ const char* mjxb_last_cuda_error(void);
 /* replaces mjx.put_model(m) + create_env_functions' closure over (sys, cfg, q0) (src/training_utils.py:105-112).
  * `blob` is the POD produced by modelc.pack_blob (struct mjxb_model_blob); copied to `device`. */
 int mjxb_model_create(const void* blob, size_t blob_bytes, const mjxb_env_config* cfg, int device, mjxb_model** out);
+/* the same with explicit option flags (mjxb_model_create derives them from MJXB_LS_ITERATIVE / MJXB_DENSE_CHOL / MJXB_INLINE_RESET in
+ * the environment, read once at create; nothing on the launch path reads the environment) */
+#define MJXB_FLAG_LS_ITERATIVE 1u  /* run MJX's bracketed line-search iteration (solver._linesearch) even where ls_iterations >= 10 would
+                                      select the closed-form exact minimiser */
+#define MJXB_FLAG_DENSE_CHOL 2u    /* dense right-looking Cholesky instead of the generated tree-ordered elimination */
+#define MJXB_FLAG_INLINE_RESET 4u  /* auto-reset runs inline instead of in deferred packed rounds */
+#define MJXB_FLAG_BUILD_EXACT 256u /* (reported only) the library is the reference-arithmetic build: no fast-math, no FMA contraction */
+int mjxb_model_create_ex(const void* blob, size_t blob_bytes, const mjxb_env_config* cfg, int device, uint32_t flags,
+                         mjxb_model** out);
+/* the options in effect for `m` (MJXB_FLAG_* bits) */
+int mjxb_model_flags(const mjxb_model* m);
+/* make the launch scratch of `stream` large enough for n_env envs now (needed before stream capture; optional otherwise) */
+int mjxb_model_reserve(const mjxb_model* m, int32_t n_env, void* stream);
 void mjxb_model_destroy(mjxb_model* m);
 /* nq, nv, nu, nbody, ncon, nefc, nsensor, obs_dim */
 int mjxb_model_dims(const mjxb_model* m, int32_t dims[8]);
-/* bytes of per-launch global scratch the library holds for constraint-row spills (allocated at create). */
+/* bytes of launch scratch currently held for `m` over all streams. */
 size_t mjxb_model_scratch_bytes(const mjxb_model* m);
 
 /* v_reset (src/envs.py:115-202,494): keys u32[n,2] (JAX threefry key data) -> state, obs[n,obs_dim]. */
@@ -185,6 +202,10 @@ int mjxb_tanh_bwd_colsum(int32_t n, int32_t c, const float* dy, const float* y, 
  * advantage / ret are [rollout_length, n_env], value is [rollout_length + 1, n_env]; device pointers, one launch. */
 int mjxb_gae(int32_t rollout_length, int32_t n_env, const float* reward, const float* value, const float* terminated,
              const float* truncated, float gamma, float lam, float* advantage, float* ret, void* stream);
+
+/* Measurement aid (bench.py's roofline_fp32 denominator): the FP32 FMA-pipe throughput of `device`, measured with a kernel of
+ * independent FFMA chains and no memory traffic (best of several repetitions; synchronises the device). */
+int mjxb_ffma_peak(int32_t device, float* tflops_out, float* ms_out);
 
 #ifdef __cplusplus
 }

@@ -6,7 +6,11 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <vector>
 
+#ifndef MJXB_EXACT
+#define MJXB_EXACT 0
+#endif
 #include "mjxb.h"
 #include "mjxb_device.cuh"
 
@@ -14,7 +18,7 @@ using namespace mjxb;
 
 namespace {
 
-constexpr int kResetPad = 148 * 16 * 2;  // per-CTA reset queues are sized in whole rounds: n_env + (CTAs x warps) entries at most
+constexpr int kMaxWarps = WARPS_MAIN > WARPS_MID ? (WARPS_MAIN > WARPS_BIG ? WARPS_MAIN : WARPS_BIG) : (WARPS_MID > WARPS_BIG ? WARPS_MID : WARPS_BIG);
 thread_local char g_cuda_err[512] = "";
 
 int cuda_fail(cudaError_t e, const char* what) {
@@ -48,15 +52,37 @@ struct Arena {  // device-resident env batch for the *_host entry points
 
 }  // namespace
 
+// Tuning switches, read ONCE at mjxb_model_create (flags argument of mjxb_model_create_ex, or the MJXB_* environment variables for
+// experiments): nothing on the launch path calls getenv.
+struct Tuning {
+  int lockstep = 1;        // 1: CTA barriers at the round top and at the solver entry / exit; 3: also at every factor/solve round; 0: none
+  int lockstep_group = 0;  // warps per barrier group (0 = the whole CTA)
+  bool inline_reset = false, sync_tiers = false;
+  bool host_direct = true, direct_obs = true, direct_scalars = true;
+  int host_chunks = 0;
+};
+
+// Per-stream launch scratch (overflow counters + lists + per-CTA reset queues). One entry per stream that has launched on the model, so
+// launches on distinct streams never share counters; an entry is never freed or resized once handed to a launch (a larger batch gets a
+// new buffer, the old one is retired until mjxb_model_destroy), so CUDA graphs captured earlier stay valid.
+struct Scratch {
+  cudaStream_t stream = nullptr;
+  int* buf = nullptr;   // [0] countA, [1] doneA, [2] countB, [3] doneB, [4..4+cap) listA (main -> mid), [4+cap..) listB (mid -> big), then reset queues
+  int cap = 0;
+};
+
 struct mjxb_model {
   DevModel host;
   DevModel* dev = nullptr;
   PairParam* dev_pp = nullptr;
   int device = 0, num_sms = 0, warps = 0, warps_mid = 0, warps_big = 0;
   size_t smem = 0, smem_mid = 0, smem_big = 0;
-  int* ovf = nullptr;   // [0] countA, [1] doneA, [2] countB, [3] doneB, [4..4+cap) listA (main -> mid), [4+cap..) listB (mid -> big)
-  int ovf_cap = 0;
+  Tuning tune;
+  mutable std::mutex scratch_mu;
+  mutable std::vector<Scratch> scratch;      // live entries, one per stream
+  mutable std::vector<int*> scratch_retired; // superseded buffers (freed at destroy)
   Arena arena;
+  size_t scratch_ints(int n_env) const { return 3 * (size_t)n_env + 4 + (size_t)num_sms * kMaxWarps * 2; }
 };
 
 namespace {
@@ -99,11 +125,11 @@ int arena_ensure(mjxb_model* m, int n) {
   int nchunk = n / 65536;
   if (nchunk < 1) nchunk = 1;
   if (nchunk > 4) nchunk = 4;
-  { const char* e = getenv("MJXB_HOST_CHUNKS"); if (e && atoi(e) > 0) nchunk = atoi(e); }
+  if (m->tune.host_chunks > 0) nchunk = m->tune.host_chunks;
   a.chunk = (n + nchunk - 1) / nchunk;
   for (int i = 0; i < Arena::kSlots; i++) {
     CU(cudaStreamCreateWithFlags(&a.pipe[i], cudaStreamNonBlocking));
-    CU(cudaMalloc(&a.pipe_ovf[i], (3 * (size_t)a.chunk + 4 + kResetPad) * sizeof(int)));
+    CU(cudaMalloc(&a.pipe_ovf[i], m->scratch_ints(a.chunk) * sizeof(int)));
     CU(cudaMemsetAsync(a.pipe_ovf[i], 0, 4 * sizeof(int), a.stream));
   }
   CU(cudaMalloc(&a.ready, Arena::kReadyMax * sizeof(unsigned)));
@@ -118,220 +144,49 @@ int arena_ensure(mjxb_model* m, int n) {
   return MJXB_OK;
 }
 
-int build_dev_model(const mjxb_model_blob& b, const mjxb_env_config* cfg, DevModel& D, PairParam* pp) {
-  memset(&D, 0, sizeof(D));
-  if (b.nv != NV) return MJXB_EUNSUPPORTED;  // the in-register factorisation is compiled for nv = 27 (humanoid family)
-  if (b.nbody > 32 || b.ngeom > 32 || b.nq > 32 || b.nlimit > 32 || b.ntlimit > 32 || b.nsensor > MJXB_MAXSENSOR) return MJXB_EUNSUPPORTED;
-  if (b.solver != 2 && b.solver != 1) return MJXB_EUNSUPPORTED;
-  D.nq = b.nq; D.nv = b.nv; D.nu = b.nu; D.nbody = b.nbody; D.njnt = b.njnt; D.ngeom = b.ngeom; D.nsite = b.nsite;
-  D.ntendon = b.ntendon; D.nsensor = b.nsensor; D.npair = b.npair; D.ncon = b.ncon; D.nefc = b.nefc; D.nlimit = b.nlimit;
-  D.ntlimit = b.ntlimit; D.ncon1 = b.ncon1; D.solver = b.solver; D.iterations = b.iterations; D.ls_iterations = b.ls_iterations;
-  D.damp_implicit = (b.integrator == 3) || (b.integrator == 0 && b.eulerdamp);
-  D.maxdepth = b.maxdepth;
-  // exact line search whenever MJX's own search is run to convergence; the truncated settings keep MJX's iteration
-  D.ls_exact = (b.ls_iterations >= 10) ? 1 : 0;
-  D.tree_chol_ok = (b.nv == kTreeNV) ? 1 : 0;
-  for (int d = 0; d < b.nv && d < kTreeNV; d++) if (b.dof_parent[d] != kTreeDofParent[d]) D.tree_chol_ok = 0;
-  if (getenv("MJXB_DENSE_CHOL")) D.tree_chol_ok = 0;
-  if (getenv("MJXB_LS_ITERATIVE")) D.ls_exact = 0;
-  D.timestep = b.timestep; D.tolerance = b.tolerance; D.ls_tolerance = b.ls_tolerance; D.meaninertia = b.meaninertia;
-  for (int k = 0; k < 3; k++) D.gravity[k] = b.gravity[k];
-  double tm = 0;
-  for (int i = 0; i < b.nbody; i++) {
-    D.body_parent[i] = b.body_parent[i]; D.body_depth[i] = b.body_depth[i]; D.body_subtree_end[i] = b.body_subtree_end[i];
-    D.body_jntadr[i] = b.body_jntadr[i]; D.body_jntnum[i] = b.body_jntnum[i];
-    for (int k = 0; k < 3; k++) { D.body_pos[i][k] = b.body_pos[i][k]; D.body_ipos[i][k] = b.body_ipos[i][k]; }
-    for (int k = 0; k < 4; k++) D.body_quat[i][k] = b.body_quat[i][k];
-    for (int k = 0; k < 6; k++) D.body_inertia[i][k] = b.body_inertia[i][k];
-    D.body_mass[i] = b.body_mass[i];
-    tm += b.body_mass[i];
-    if (i >= 1) {  // single kinematic tree rooted at body 1 (one subtree_com reference point)
-      int r = i;
-      while (b.body_parent[r] != 0) r = b.body_parent[r];
-      if (r != 1) return MJXB_EUNSUPPORTED;
-    }
-  }
-  D.total_mass = (float)tm;
-  for (int j = 0; j < b.njnt; j++) {
-    D.jnt_type[j] = b.jnt_type[j]; D.jnt_qposadr[j] = b.jnt_qposadr[j]; D.jnt_dofadr[j] = b.jnt_dofadr[j];
-    for (int k = 0; k < 3; k++) { D.jnt_pos[j][k] = b.jnt_pos[j][k]; D.jnt_axis[j][k] = b.jnt_axis[j][k]; }
-    if (b.jnt_type[j] != 0 && b.jnt_type[j] != 3) return MJXB_EUNSUPPORTED;
-  }
-  for (int i = 0; i < b.nlimit; i++) {
-    int j = b.lim_jnt[i];
-    D.lim_dof[i] = b.jnt_dofadr[j]; D.lim_qadr[i] = b.jnt_qposadr[j]; D.lim_row[i] = i;
-    D.lim_range[i][0] = b.jnt_range[j][0]; D.lim_range[i][1] = b.jnt_range[j][1];
-    D.lim_invweight[i] = b.dof_invweight0[b.jnt_dofadr[j]];
-    for (int k = 0; k < 2; k++) D.lim_solref[i][k] = b.jnt_solref[j][k];
-    for (int k = 0; k < 5; k++) D.lim_solimp[i][k] = b.jnt_solimp[j][k];
-  }
-  for (int d = 0; d < MJXB_MAXDOF; d++) { D.dof_act[d] = -1; D.dof_qadr[d] = -1; D.dof_parent[d] = -1; }
-  for (int d = 0; d < b.nv; d++) {
-    D.dof_body[d] = b.dof_body[d]; D.dof_jnt[d] = b.dof_jnt[d]; D.dof_parent[d] = b.dof_parent[d];
-    D.dof_armature[d] = b.dof_armature[d]; D.dof_damping[d] = b.dof_damping[d]; D.dof_stiffness[d] = b.dof_stiffness[d];
-    int j = b.dof_jnt[d];
-    if (b.jnt_type[j] == 3) D.dof_qadr[d] = b.jnt_qposadr[j];
-  }
-  for (int u = 0; u < b.nu; u++) {
-    int d = b.act_dof[u];
-    if (D.dof_act[d] >= 0) return MJXB_EUNSUPPORTED;  // one motor per dof
-    D.dof_act[d] = u; D.dof_gear[d] = b.act_gear[u];
-    D.dof_ctrl_lo[d] = b.act_ctrllimited[u] ? b.act_ctrlrange[u][0] : -3.0e38f;
-    D.dof_ctrl_hi[d] = b.act_ctrllimited[u] ? b.act_ctrlrange[u][1] : 3.0e38f;
-  }
-  for (int i = 0; i < b.nq; i++) { D.qpos0[i] = b.qpos0[i]; D.qpos_spring[i] = b.qpos_spring[i]; }
-  for (int j = 0; j < b.njnt; j++) {
-    int qa = b.jnt_qposadr[j], da = b.jnt_dofadr[j];
-    if (b.jnt_type[j] == 0) {
-      for (int k = 0; k < 3; k++) { D.qpos_kind[qa + k] = QK_FREEPOS; D.qpos_aux[qa + k] = da + k; }
-      for (int k = 0; k < 4; k++) { D.qpos_kind[qa + 3 + k] = QK_FREEQUAT; D.qpos_aux[qa + 3 + k] = (qa + 3) | (k << 8) | ((da + 3) << 16); }
-    } else {
-      D.qpos_kind[qa] = QK_HINGE; D.qpos_aux[qa] = da;
-    }
-  }
-  // joint tree + body/dof tables for the prefix-composition kinematics
-  {
-    int body_lastjnt[MJXB_MAXBODY];
-    for (int i = 0; i < b.nbody; i++) body_lastjnt[i] = b.body_jntnum[i] > 0 ? b.body_jntadr[i] + b.body_jntnum[i] - 1 : -1;
-    int maxchain = 1;
-    for (int j = 0; j < b.njnt; j++) {
-      const int bd = b.jnt_body[j];
-      D.jnt_bodyid[j] = bd;
-      D.jnt_first[j] = (j == b.body_jntadr[bd]) ? 1 : 0;
-      int par = -1;
-      if (!D.jnt_first[j]) par = j - 1;
-      else {
-        int a = b.body_parent[bd];
-        // fixed offsets of joint-less bodies between bd and its nearest jointed ancestor are not supported for a FIRST joint
-        if (a > 0 && body_lastjnt[a] < 0) return MJXB_EUNSUPPORTED;
-        par = a > 0 ? body_lastjnt[a] : -1;
-      }
-      if (b.jnt_type[j] == 0 && (par >= 0 || b.body_parent[bd] != 0)) return MJXB_EUNSUPPORTED;  // free joints only on top-level bodies
-      D.jnt_parent[j] = par;
-    }
-    for (int j = 0; j < b.njnt; j++) { int n = 1; for (int a = D.jnt_parent[j]; a >= 0; a = D.jnt_parent[a]) n++; if (n > maxchain) maxchain = n; }
-    for (int d = 0; d < b.nv; d++) { int n = 1; for (int a = b.dof_parent[d]; a >= 0; a = b.dof_parent[a]) n++; if (n > maxchain) maxchain = n; }
-    D.tree_steps = 0;
-    while ((1 << D.tree_steps) < maxchain) D.tree_steps++;
-    for (int i = 0; i < b.nbody; i++) {
-      // body frame = frame after joint srcjnt composed with (relpos, relquat); joint-less bodies accumulate their fixed offsets
-      double rp[3] = {0, 0, 0}, rq[4] = {1, 0, 0, 0};
-      int a = i;
-      while (a > 0 && body_lastjnt[a] < 0) {  // prepend body a's offset: T_a o (rp, rq)
-        const double w = b.body_quat[a][0], x = b.body_quat[a][1], y = b.body_quat[a][2], z = b.body_quat[a][3];
-        const double R[9] = {w * w + x * x - y * y - z * z, 2 * (x * y - w * z), 2 * (x * z + w * y), 2 * (x * y + w * z), w * w - x * x + y * y - z * z,
-                             2 * (y * z - w * x), 2 * (x * z - w * y), 2 * (y * z + w * x), w * w - x * x - y * y + z * z};
-        const double np[3] = {b.body_pos[a][0] + R[0] * rp[0] + R[1] * rp[1] + R[2] * rp[2], b.body_pos[a][1] + R[3] * rp[0] + R[4] * rp[1] + R[5] * rp[2],
-                              b.body_pos[a][2] + R[6] * rp[0] + R[7] * rp[1] + R[8] * rp[2]};
-        const double nq[4] = {w * rq[0] - x * rq[1] - y * rq[2] - z * rq[3], w * rq[1] + x * rq[0] + y * rq[3] - z * rq[2],
-                              w * rq[2] - x * rq[3] + y * rq[0] + z * rq[1], w * rq[3] + x * rq[2] - y * rq[1] + z * rq[0]};
-        for (int k = 0; k < 3; k++) rp[k] = np[k];
-        for (int k = 0; k < 4; k++) rq[k] = nq[k];
-        a = b.body_parent[a];
-      }
-      D.body_srcjnt[i] = a > 0 ? body_lastjnt[a] : -1;
-      for (int k = 0; k < 3; k++) D.body_relpos[i][k] = (float)rp[k];
-      for (int k = 0; k < 4; k++) D.body_relquat[i][k] = (float)rq[k];
-      int bb = i;
-      while (bb > 0 && b.body_dofnum[bb] == 0) bb = b.body_parent[bb];
-      D.body_lastdof[i] = bb > 0 ? b.body_dofadr[bb] + b.body_dofnum[bb] - 1 : -1;
-    }
-    for (int d = 0; d < MJXB_MAXDOF; d++) D.dof_cvel_src[d] = -2;
-    for (int d = 0; d < b.nv; d++) {
-      const int j = b.dof_jnt[d];
-      if (b.jnt_type[j] == 0) {
-        const int k = d - b.jnt_dofadr[j];
-        D.dof_cvel_src[d] = k < 3 ? -2 : b.jnt_dofadr[j] + 2;   // linear: cdof_dot = 0; angular: velocity after the three linear dofs
-      } else {
-        D.dof_cvel_src[d] = b.dof_parent[d];                    // -1: nothing moves before this dof
-      }
-    }
-  }
-  // dofs that move each body: walk the dof-parent chain from the body's (or nearest jointed ancestor's) last dof
-  for (int i = 1; i < b.nbody; i++) {
-    int bb = i;
-    while (bb > 0 && b.body_dofnum[bb] == 0) bb = b.body_parent[bb];
-    uint32_t mask = 0;
-    if (bb > 0)
-      for (int d = b.body_dofadr[bb] + b.body_dofnum[bb] - 1; d >= 0; d = b.dof_parent[d]) mask |= 1u << d;
-    D.body_dofmask[i] = mask;
-  }
-  for (int g = 0; g < b.ngeom; g++) {
-    D.geom_body[g] = b.geom_body[g];
-    for (int k = 0; k < 3; k++) D.geom_pos[g][k] = b.geom_pos[g][k];
-    // local z axis of the geom frame (third column of the rotation of geom_quat), in double
-    double w = b.geom_quat[g][0], x = b.geom_quat[g][1], y = b.geom_quat[g][2], z = b.geom_quat[g][3];
-    D.geom_axis[g][0] = (float)(2 * (x * z + w * y)); D.geom_axis[g][1] = (float)(2 * (y * z - w * x));
-    D.geom_axis[g][2] = (float)(w * w - x * x - y * y + z * z);
-    D.geom_rad[g] = b.geom_size[g][0]; D.geom_half[g] = b.geom_size[g][1];
-    if (b.geom_type[g] == 0) { D.geom_rad[g] = 0.0f; D.geom_half[g] = 0.0f; }
-  }
-  if (b.npair > MJXB_MAXPAIR || b.ncon > MAXCC_BIG || b.nefc > CAP_BIG) return MJXB_EUNSUPPORTED;
-  for (int p = 0; p < b.npair; p++) {
-    D.pair_w0[p] = (uint32_t)b.pair_g1[p] | ((uint32_t)b.pair_g2[p] << 8) | ((uint32_t)b.pair_kind[p] << 16) | ((uint32_t)b.pair_condim[p] << 24);
-    {  // bit 31: the two bodies sit on different limbs (neither dof chain contains the other): such a row breaks the tree pattern of H
-      const uint32_t m1 = D.body_dofmask[b.geom_body[b.pair_g1[p]]], m2 = D.body_dofmask[b.geom_body[b.pair_g2[p]]];
-      if ((m1 & m2) != m1 && (m1 & m2) != m2) D.pair_w0[p] |= 0x80000000u;
-    }
-    D.pair_w1[p] = (uint32_t)b.pair_conadr[p] | ((uint32_t)b.pair_efcadr[p] << 16);
-    pp[p].mu = b.pair_mu[p]; pp[p].invweight = b.pair_invweight[p];
-    for (int k = 0; k < 2; k++) pp[p].solref[k] = b.pair_solref[p][k];
-    for (int k = 0; k < 5; k++) pp[p].solimp[k] = b.pair_solimp[p][k];
-    if (b.pair_condim[p] != 1 && b.pair_condim[p] != 3) return MJXB_EUNSUPPORTED;
-  }
-  for (int i = 0; i < b.ntlimit; i++) {
-    int t = b.lim_ten[i];
-    D.ten_nwrap[i] = b.ten_nwrap[t]; D.ten_row[i] = b.nlimit + i;
-    for (int w = 0; w < MJXB_MAXWRAP; w++) { D.ten_dof[i][w] = b.ten_dof[t][w]; D.ten_qpos[i][w] = b.ten_qpos[t][w]; D.ten_coef[i][w] = b.ten_coef[t][w]; }
-    for (int k = 0; k < 2; k++) { D.ten_range[i][k] = b.ten_range[t][k]; D.ten_solref[i][k] = b.ten_solref[t][k]; }
-    for (int k = 0; k < 5; k++) D.ten_solimp[i][k] = b.ten_solimp[t][k];
-    D.ten_invweight[i] = b.ten_invweight0[t];
-  }
-  for (int s = 0; s < b.nsite; s++) {
-    D.site_body[s] = b.site_body[s];
-    for (int k = 0; k < 3; k++) { D.site_pos[s][k] = b.site_pos[s][k]; D.site_size[s][k] = b.site_size[s][k]; }
-    for (int k = 0; k < 4; k++) D.site_quat[s][k] = b.site_quat[s][k];
-  }
-  for (int s = 0; s < b.nsensor; s++) D.sensor_site[s] = b.sensor_site[s];
-  if (cfg) {
-    D.cfg = *cfg;
-    if (cfg->obs_dim != 1 + 3 + (b.nq - 7) + b.nv + 2 || cfg->obs_dim > MJXB_MAXOBS) return MJXB_EINVAL;
-    if (cfg->pelvis_body_id < 0 || cfg->pelvis_body_id >= b.nbody || cfg->head_body_id < 0 || cfg->head_body_id >= b.nbody) return MJXB_EINVAL;
-    if (cfg->touch_sensor_right_id < 0 || cfg->touch_sensor_right_id >= b.nsensor || cfg->touch_sensor_left_id < 0 ||
-        cfg->touch_sensor_left_id >= b.nsensor) return MJXB_EINVAL;
-    for (int i = 0; i < b.nu; i++) if (cfg->act_perm[i] < 0 || cfg->act_perm[i] >= b.nu) return MJXB_EINVAL;
-    for (int i = 0; i < cfg->obs_dim; i++) if (cfg->obs_perm[i] < 0 || cfg->obs_perm[i] >= cfg->obs_dim) return MJXB_EINVAL;
-  } else {
-    D.cfg.obs_dim = 1 + 3 + (b.nq - 7) + b.nv + 2;
-    D.cfg.pelvis_body_id = 0; D.cfg.head_body_id = 0;
-  }
-  return MJXB_OK;
-}
 
 using KMain = void (*)(const DevModel*, const PairParam*, StepArgs);
 
-int launch(const mjxb_model* mc, const StepArgs& args_in, bool dbg, cudaStream_t stream, int* ovf_buf = nullptr, int ovf_buf_cap = 0) {
-  mjxb_model* m = const_cast<mjxb_model*>(mc);  // the overflow list is library-owned scratch, grown on first use for a batch size
+// the stream's scratch entry, created / grown here (never while the stream is capturing: mjxb_model_reserve must have run before)
+int scratch_for(const mjxb_model* m, cudaStream_t stream, int n_env, int** buf, int* cap) {
+  std::lock_guard<std::mutex> lock(m->scratch_mu);
+  Scratch* s = nullptr;
+  for (Scratch& e : m->scratch) if (e.stream == stream) { s = &e; break; }
+  if (s != nullptr && s->cap >= n_env) { *buf = s->buf; *cap = s->cap; return MJXB_OK; }
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &cs) != cudaSuccess) cudaGetLastError();
+  if (cs != cudaStreamCaptureStatusNone) {
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "launch scratch for %d envs is missing on a capturing stream: call mjxb_model_reserve first", n_env);
+    return MJXB_ECUDA;
+  }
+  int* nb = nullptr;
+  CU(cudaMalloc(&nb, m->scratch_ints(n_env) * sizeof(int)));
+  CU(cudaMemsetAsync(nb, 0, 4 * sizeof(int), stream));
+  if (s == nullptr) { m->scratch.push_back(Scratch()); s = &m->scratch.back(); s->stream = stream; }
+  else m->scratch_retired.push_back(s->buf);  // earlier launches / captured graphs may still reference it
+  s->buf = nb; s->cap = n_env;
+  *buf = nb; *cap = n_env;
+  return MJXB_OK;
+}
+
+int launch(const mjxb_model* m, const StepArgs& args_in, bool dbg, cudaStream_t stream, int* ovf_buf = nullptr, int ovf_buf_cap = 0) {
   int cur = 0;
   CU(cudaGetDevice(&cur));
   if (cur != m->device) CU(cudaSetDevice(m->device));
-  if (ovf_buf == nullptr && m->ovf_cap < args_in.n_env) {
-    if (m->ovf) { CU(cudaStreamSynchronize(stream)); CU(cudaFree(m->ovf)); m->ovf = nullptr; }
-    CU(cudaMalloc(&m->ovf, (3 * (size_t)args_in.n_env + 4 + kResetPad) * sizeof(int)));
-    CU(cudaMemsetAsync(m->ovf, 0, 4 * sizeof(int), stream));
-    m->ovf_cap = args_in.n_env;
+  int* ovf = ovf_buf;
+  int cap = ovf_buf_cap;
+  if (ovf == nullptr) {
+    const int rc = scratch_for(m, stream, args_in.n_env, &ovf, &cap);
+    if (rc != MJXB_OK) { if (cur != m->device) cudaSetDevice(cur); return rc; }
   }
   StepArgs args = args_in;
-  int* ovf = ovf_buf ? ovf_buf : m->ovf;
-  const int cap = ovf_buf ? ovf_buf_cap : m->ovf_cap;
   int* listA = ovf + 4;
   int* listB = ovf + 4 + cap;
   args.in_count = nullptr; args.in_list = nullptr; args.in_done = nullptr; args.out_count = ovf; args.out_list = listA;
-  args.reset_list = (getenv("MJXB_INLINE_RESET") != nullptr) ? nullptr : ovf + 4 + 2 * (size_t)cap;
+  args.reset_list = m->tune.inline_reset ? nullptr : ovf + 4 + 2 * (size_t)cap;
   // 1 (default): CTA barriers at the round top and at the solver entry / exit; 3: additionally at every factor/solve round (was the
   // better choice before the solver's dependent chains were shortened: 35.2 M against 36.4 M now); 0: none (profiling aid)
-  { const char* e = getenv("MJXB_LOCKSTEP"); args.lockstep = e ? atoi(e) : 1; }
-  { const char* e = getenv("MJXB_LOCKSTEP_GROUP"); args.lockstep_group = e ? atoi(e) : 0; }
+  args.lockstep = m->tune.lockstep; args.lockstep_group = m->tune.lockstep_group;
   // small batches: spread the envs over every SM (fewer warps per CTA run faster than 16 sharing one SM's issue slots)
   int warps = m->warps;
   const int per_sm = (args.n_env + m->num_sms - 1) / m->num_sms;
@@ -353,7 +208,7 @@ int launch(const mjxb_model* mc, const StepArgs& args_in, bool dbg, cudaStream_t
   if (single) mjxb_step_kernel<false, CAP_MAIN, MAXCC_MAIN, WARPS_MAIN, true, true><<<grid, warps * 32, smem_main, stream>>>(m->dev, m->dev_pp, args);
   else MJXB_LAUNCH(CAP_MAIN, MAXCC_MAIN, WARPS_MAIN, grid, warps * 32, smem_main);
   cudaError_t e = cudaGetLastError();
-  const bool sync_tiers = getenv("MJXB_SYNC_TIERS") != nullptr;  // debugging aid: attribute a device fault to its tier
+  const bool sync_tiers = m->tune.sync_tiers;  // debugging aid: attribute a device fault to its tier
   if (sync_tiers && e == cudaSuccess) { e = cudaStreamSynchronize(stream); if (e != cudaSuccess) fprintf(stderr, "[mjxb] main tier failed: %s\n", cudaGetErrorString(e)); }
   args.in_ready = nullptr;  // only the first pass waits for streamed inputs
   if (e == cudaSuccess) {  // mid tier (64 rows / 24 contacts) over the envs the main tile could not hold; usually few: exits at once when empty
@@ -406,7 +261,18 @@ const char* mjxb_strerror(int code) {
   }
 }
 
+static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+
 int mjxb_model_create(const void* blob, size_t blob_bytes, const mjxb_env_config* cfg, int device, mjxb_model** out) {
+  // the experiment switches of the environment are folded into flags here, once
+  uint32_t flags = 0;
+  if (getenv("MJXB_LS_ITERATIVE")) flags |= MJXB_FLAG_LS_ITERATIVE;
+  if (getenv("MJXB_DENSE_CHOL")) flags |= MJXB_FLAG_DENSE_CHOL;
+  if (getenv("MJXB_INLINE_RESET")) flags |= MJXB_FLAG_INLINE_RESET;
+  return mjxb_model_create_ex(blob, blob_bytes, cfg, device, flags, out);
+}
+
+int mjxb_model_create_ex(const void* blob, size_t blob_bytes, const mjxb_env_config* cfg, int device, uint32_t flags, mjxb_model** out) {
   if (!blob || !out) return MJXB_EINVAL;
   *out = nullptr;
   if (blob_bytes != sizeof(mjxb_model_blob)) return MJXB_EBLOB;
@@ -423,6 +289,24 @@ int mjxb_model_create(const void* blob, size_t blob_bytes, const mjxb_env_config
   memset(pp, 0, sizeof(pp));
   int rc = build_dev_model(b, cfg, m->host, pp);
   if (rc != MJXB_OK) { delete m; return rc; }
+  {  // the generated leaves-first elimination (mjxb_chol_tree.cuh) applies when the model's dof tree is the one it was generated for
+    DevModel& D = m->host;
+    D.tree_chol_ok = (b.nv == kTreeNV) ? 1 : 0;
+    for (int d = 0; d < b.nv && d < kTreeNV; d++) if (b.dof_parent[d] != kTreeDofParent[d]) D.tree_chol_ok = 0;
+    if (flags & MJXB_FLAG_DENSE_CHOL) D.tree_chol_ok = 0;
+#if MJXB_EXACT
+    D.ls_exact = 0;  // the reference-arithmetic build always runs MJX's bracketed line search
+#endif
+    if (flags & MJXB_FLAG_LS_ITERATIVE) D.ls_exact = 0;
+  }
+  m->tune.inline_reset = (flags & MJXB_FLAG_INLINE_RESET) != 0;
+  m->tune.lockstep = env_int("MJXB_LOCKSTEP", 1);
+  m->tune.lockstep_group = env_int("MJXB_LOCKSTEP_GROUP", 0);
+  m->tune.sync_tiers = getenv("MJXB_SYNC_TIERS") != nullptr;
+  m->tune.host_chunks = env_int("MJXB_HOST_CHUNKS", 0);
+  m->tune.host_direct = env_int("MJXB_HOST_DIRECT", 1) != 0;
+  m->tune.direct_obs = env_int("MJXB_DIRECT_OBS", 1) != 0;
+  m->tune.direct_scalars = env_int("MJXB_DIRECT_SCALARS", 1) != 0;
   m->device = device;
   cudaError_t e;
 #define CUX(call) if ((e = (call)) != cudaSuccess) { cuda_fail(e, #call); mjxb_model_destroy(m); return MJXB_ECUDA; }
@@ -469,7 +353,8 @@ void mjxb_model_destroy(mjxb_model* m) {
   arena_free(m->arena);
   if (m->dev) cudaFree(m->dev);
   if (m->dev_pp) cudaFree(m->dev_pp);
-  if (m->ovf) cudaFree(m->ovf);
+  for (Scratch& e : m->scratch) if (e.buf) cudaFree(e.buf);
+  for (int* p : m->scratch_retired) if (p) cudaFree(p);
   delete m;
 }
 
@@ -481,7 +366,37 @@ int mjxb_model_dims(const mjxb_model* m, int32_t dims[8]) {
   return MJXB_OK;
 }
 
-size_t mjxb_model_scratch_bytes(const mjxb_model* m) { return m ? (3 * (size_t)m->ovf_cap + 4 + kResetPad) * sizeof(int) : 0; }
+size_t mjxb_model_scratch_bytes(const mjxb_model* m) {
+  if (!m) return 0;
+  std::lock_guard<std::mutex> lock(m->scratch_mu);
+  size_t total = 0;
+  for (const Scratch& e : m->scratch) total += m->scratch_ints(e.cap) * sizeof(int);
+  return total;
+}
+
+int mjxb_model_reserve(const mjxb_model* m, int32_t n_env, void* stream) {
+  if (!m || n_env <= 0) return MJXB_EINVAL;
+  int cur = 0;
+  CU(cudaGetDevice(&cur));
+  if (cur != m->device) CU(cudaSetDevice(m->device));
+  int* buf = nullptr;
+  int cap = 0;
+  const int rc = scratch_for(m, (cudaStream_t)stream, n_env, &buf, &cap);
+  if (cur != m->device) cudaSetDevice(cur);
+  return rc;
+}
+
+int mjxb_model_flags(const mjxb_model* m) {
+  if (!m) return MJXB_EINVAL;
+  int f = 0;
+  if (!m->host.ls_exact) f |= MJXB_FLAG_LS_ITERATIVE;
+  if (!m->host.tree_chol_ok) f |= MJXB_FLAG_DENSE_CHOL;
+  if (m->tune.inline_reset) f |= MJXB_FLAG_INLINE_RESET;
+#if MJXB_EXACT
+  f |= MJXB_FLAG_BUILD_EXACT;
+#endif
+  return f;
+}
 
 #if MJXB_STAGE_CLOCK
 int mjxb_debug_stage_clock(int32_t* host_out, int32_t n_env) {  // profiling variant only (not part of include/mjxb.h)
@@ -595,7 +510,7 @@ static int step_host_impl(mjxb_model* m, int32_t n_env, const float* action_host
   // on the copy stream in ~8 chunks, each followed by a 4-byte flag copy the kernel waits on (copy engines only: a flag *kernel* could
   // never be scheduled beside the persistent grid); obs are stored by the kernel straight into the caller's mapped buffer.
   void *obs_dev = nullptr, *tmp = nullptr;
-  const bool direct = getenv("MJXB_HOST_DIRECT") ? atoi(getenv("MJXB_HOST_DIRECT")) != 0 : true;
+  const bool direct = m->tune.host_direct;
   if (direct && host_dev_ptr(obs_host, &obs_dev) && host_dev_ptr(action_host, &tmp) && (!keys_host || host_dev_ptr(keys_host, &tmp))) {
     cudaStream_t main_st = a.pipe[0], copy_st = a.pipe[1];
     a.epoch++;
@@ -614,8 +529,7 @@ static int step_host_impl(mjxb_model* m, int32_t n_env, const float* action_host
     sa.terminated = a.term; sa.truncated = a.trunc;
     sa.in_ready = a.ready; sa.in_ready_shift = a.ready_shift; sa.in_ready_epoch = a.epoch;
     sa.in_timeout = a.ready_src + Arena::kReadyMax;  // pinned: the same address is valid on the device (UVA)
-    const bool obs_direct = getenv("MJXB_DIRECT_OBS") ? atoi(getenv("MJXB_DIRECT_OBS")) != 0 : true;
-    const bool sc_direct = getenv("MJXB_DIRECT_SCALARS") ? atoi(getenv("MJXB_DIRECT_SCALARS")) != 0 : true;
+    const bool obs_direct = m->tune.direct_obs, sc_direct = m->tune.direct_scalars;
     void *rd = nullptr, *td = nullptr, *ud = nullptr;
     const bool scd = sc_direct && host_dev_ptr(reward_host, &rd) && host_dev_ptr(terminated_host, &td) && host_dev_ptr(truncated_host, &ud);
     if (!obs_direct) sa.obs = a.obs;

@@ -15,70 +15,13 @@
 #include <stdint.h>
 
 #include "mjxb.h"
+#include "mjxb_model_dev.h"
 
 namespace mjxb {
 
-constexpr int NV = 27;    // compile-time dof count: the register-resident factorisation is statically unrolled
-constexpr int NVP = 28;   // row stride (floats) of M and J: 16-byte aligned rows for 128-bit loads
-// Main instantiation: candidate constraint rows / candidate contacts held in shared memory per env. An env that needs
-// more is appended to an overflow list and re-run by the BIG instantiation (capacity >= every static row of the model).
-#ifndef MJXB_CAP_MAIN
-#define MJXB_CAP_MAIN 32
-#define MJXB_MAXCC_MAIN 16
-#ifndef MJXB_WARPS_MAIN
-#define MJXB_WARPS_MAIN 16
-#endif
-#endif
-constexpr int CAP_MAIN = MJXB_CAP_MAIN, MAXCC_MAIN = MJXB_MAXCC_MAIN, WARPS_MAIN = MJXB_WARPS_MAIN;
-constexpr int CAP_MID = 64, MAXCC_MID = 24, WARPS_MID = 10;
-constexpr int CAP_BIG = 320, MAXCC_BIG = 176, WARPS_BIG = 3;
 constexpr unsigned FULL = 0xffffffffu;
-constexpr float MINVAL = 1e-15f;
 
-enum { MODE_ENV_STEP = 0, MODE_ENV_RESET = 1, MODE_PHYS_STEP = 2, MODE_FORWARD = 3, MODE_SPEED_TEST = 4 };
-enum { PAIR_PLANE_SPHERE = 0, PAIR_PLANE_CAPSULE = 1, PAIR_SPHERE_SPHERE = 2, PAIR_SPHERE_CAPSULE = 3, PAIR_CAPSULE_CAPSULE = 4 };
-enum { ROW_LIMIT = 0, ROW_TENDON = 1, ROW_CON1 = 2, ROW_CON3 = 3 };
-enum { QK_HINGE = 0, QK_FREEPOS = 1, QK_FREEQUAT = 2 };
-
-struct PairParam { float mu, invweight, solref[2], solimp[5]; };
-
-// Device copy of the model: the fields of mjxb_model_blob the kernels need, plus derived tables.
-struct DevModel {
-  int nq, nv, nu, nbody, njnt, ngeom, nsite, ntendon, nsensor, npair, ncon, nefc, nlimit, ntlimit, ncon1;
-  int solver, iterations, ls_iterations, damp_implicit, maxdepth, ls_exact;
-  float timestep, gravity[3], tolerance, ls_tolerance, meaninertia, total_mass;
-  int body_parent[MJXB_MAXBODY], body_depth[MJXB_MAXBODY], body_subtree_end[MJXB_MAXBODY], body_jntadr[MJXB_MAXBODY],
-      body_jntnum[MJXB_MAXBODY];
-  uint32_t body_dofmask[MJXB_MAXBODY];  // dofs that move the body (ancestors-or-self)
-  float body_pos[MJXB_MAXBODY][3], body_quat[MJXB_MAXBODY][4], body_ipos[MJXB_MAXBODY][3], body_inertia[MJXB_MAXBODY][6],
-      body_mass[MJXB_MAXBODY];
-  int jnt_type[MJXB_MAXJNT], jnt_qposadr[MJXB_MAXJNT], jnt_dofadr[MJXB_MAXJNT];
-  int jnt_parent[MJXB_MAXJNT], jnt_first[MJXB_MAXJNT], jnt_bodyid[MJXB_MAXJNT];  // joint tree (previous joint up the chain), first joint of its body
-  int body_srcjnt[MJXB_MAXBODY], body_lastdof[MJXB_MAXBODY];  // joint whose frame carries the body; last dof moving the body (-1: none)
-  float body_relpos[MJXB_MAXBODY][3], body_relquat[MJXB_MAXBODY][4];  // fixed offset of the body frame from that joint frame
-  int dof_cvel_src[MJXB_MAXDOF];  // dof whose inclusive velocity prefix is 'cvel before this dof' (-1: zero, -2: cdof_dot = 0)
-  int tree_steps;  // pointer-jumping rounds covering the deepest joint / dof chain
-  int tree_chol_ok;  // the model's dof tree is the one mjxb_chol_tree.cuh was generated for
-  float jnt_pos[MJXB_MAXJNT][3], jnt_axis[MJXB_MAXJNT][3];
-  int lim_dof[MJXB_MAXJNT], lim_qadr[MJXB_MAXJNT], lim_row[MJXB_MAXJNT];
-  float lim_range[MJXB_MAXJNT][2], lim_invweight[MJXB_MAXJNT], lim_solref[MJXB_MAXJNT][2], lim_solimp[MJXB_MAXJNT][5];
-  int dof_body[MJXB_MAXDOF], dof_jnt[MJXB_MAXDOF], dof_parent[MJXB_MAXDOF], dof_qadr[MJXB_MAXDOF], dof_act[MJXB_MAXDOF];
-  float dof_armature[MJXB_MAXDOF], dof_damping[MJXB_MAXDOF], dof_stiffness[MJXB_MAXDOF], dof_gear[MJXB_MAXDOF],
-      dof_ctrl_lo[MJXB_MAXDOF], dof_ctrl_hi[MJXB_MAXDOF];
-  int qpos_kind[MJXB_MAXQ], qpos_aux[MJXB_MAXQ];  // integrator addressing: hinge -> dof; free pos -> dof; free quat -> (qadr | comp<<8 | dof<<16)
-  float qpos0[MJXB_MAXQ], qpos_spring[MJXB_MAXQ];
-  int geom_body[MJXB_MAXGEOM];
-  float geom_pos[MJXB_MAXGEOM][3], geom_axis[MJXB_MAXGEOM][3], geom_rad[MJXB_MAXGEOM], geom_half[MJXB_MAXGEOM];
-  uint32_t pair_w0[MJXB_MAXPAIR];  // g1 | g2<<8 | kind<<16 | condim<<24
-  uint32_t pair_w1[MJXB_MAXPAIR];  // conadr | efcadr<<16
-  int ten_nwrap[MJXB_MAXTENDON], ten_dof[MJXB_MAXTENDON][MJXB_MAXWRAP], ten_qpos[MJXB_MAXTENDON][MJXB_MAXWRAP], ten_row[MJXB_MAXTENDON];
-  float ten_coef[MJXB_MAXTENDON][MJXB_MAXWRAP], ten_range[MJXB_MAXTENDON][2], ten_solref[MJXB_MAXTENDON][2],
-      ten_solimp[MJXB_MAXTENDON][5], ten_invweight[MJXB_MAXTENDON];
-  int site_body[MJXB_MAXSITE], sensor_site[MJXB_MAXSENSOR];
-  float site_pos[MJXB_MAXSITE][3], site_quat[MJXB_MAXSITE][4], site_size[MJXB_MAXSITE][3];
-  mjxb_env_config cfg;
-  int pad_[1];
-};
+static_assert(sizeof(DevModel) % 16 == 0, "DevModel is staged into shared memory with 16-byte copies");
 
 struct StepArgs {
   int n_env, mode, nsteps, autoreset;

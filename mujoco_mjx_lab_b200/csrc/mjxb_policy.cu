@@ -12,6 +12,7 @@
 //   B (weights W^T, N rows x K):     byte(n,k) = (n%8)*16 + (n/8)*(K/8)*128 + (k/8)*128 + (k%8)*2 -> SBO = 16*K, LBO = 128
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <mutex>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -302,9 +303,56 @@ __global__ void tanh_bwd_colsum_kernel(int n, int c, const float* __restrict__ d
   }
 }
 
+// FP32 FMA-pipe ceiling, measured: 8 independent FFMA chains per thread (no memory traffic), 1024 threads per CTA, 2 CTAs per SM.
+__global__ void __launch_bounds__(1024, 2) ffma_peak_kernel(float* sink, int iters, float seed) {
+  float a0 = seed + threadIdx.x, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+  const float m = 0.999999f, c = 1e-7f * seed;
+#pragma unroll 1
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+      a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+      a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+    }
+  }
+  const float r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (r == 123.456f) sink[0] = r;   // never true: keeps the chains alive
+}
+
 }  // namespace mjxbp
 
 extern "C" {
+
+int mjxb_ffma_peak(int32_t device, float* tflops_out, float* ms_out) {
+  if (!tflops_out) return MJXB_EINVAL;
+  int cur = 0, nsm = 0;
+  if (cudaGetDevice(&cur) != cudaSuccess) { cudaGetLastError(); return MJXB_ENOGPU; }
+  if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return MJXB_EINVAL; }
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
+  float* sink = nullptr;
+  cudaEvent_t e0, e1;
+  if (cudaMalloc(&sink, 4) != cudaSuccess) { cudaGetLastError(); cudaSetDevice(cur); return MJXB_ECUDA; }
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const int grid = nsm * 2, iters = 4096;
+  float best = 1e30f;
+  for (int rep = 0; rep < 6; rep++) {   // first repetitions warm up clocks / instruction cache; best of the rest
+    cudaEventRecord(e0, 0);
+    mjxbp::ffma_peak_kernel<<<grid, 1024>>>(sink, iters, 1.0f + rep);
+    cudaEventRecord(e1, 0);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep >= 2 && ms < best) best = ms;
+  }
+  const cudaError_t err = cudaGetLastError();
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+  cudaSetDevice(cur);
+  if (err != cudaSuccess) return MJXB_ECUDA;
+  const double flops = 2.0 * 8 * 16 * (double)iters * 1024.0 * grid;
+  *tflops_out = (float)(flops / (best * 1e-3) / 1e12);
+  if (ms_out) *ms_out = best;
+  return MJXB_OK;
+}
 
 int mjxb_tanh_bwd_colsum(int32_t n, int32_t c, const float* dy, const float* y, float* dz, float* db_zeroed, void* stream) {
   if (n <= 0 || c <= 0 || !dy || !db_zeroed || (y != nullptr && dz == nullptr)) return MJXB_EINVAL;
@@ -336,13 +384,19 @@ int mjxb_policy_act(int32_t n_env, int32_t obs_dim, int32_t act_dim, const float
   if (n_env <= 0 || !obs || !w_packed || !bias || !log_std || !eps || !act || !logp) return MJXB_EINVAL;
   if (obs_dim <= 0 || obs_dim > mjxbp::kInPad || act_dim <= 0 || act_dim > mjxbp::kOutPad) return MJXB_EUNSUPPORTED;
   if ((rms_mean == nullptr) != (rms_var == nullptr)) return MJXB_EINVAL;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(mjxbp::policy_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mjxbp::kSmemBytes) != cudaSuccess) {
-      cudaGetLastError();
-      return MJXB_ECUDA;
+  {  // the opt-in shared-memory size is a per-device function attribute: set it once per device, thread-safely
+    static std::mutex mu;
+    static bool attr_set[64] = {};
+    int devid = 0;
+    if (cudaGetDevice(&devid) != cudaSuccess || devid < 0 || devid >= 64) { cudaGetLastError(); return MJXB_ECUDA; }
+    std::lock_guard<std::mutex> lock(mu);
+    if (!attr_set[devid]) {
+      if (cudaFuncSetAttribute(mjxbp::policy_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mjxbp::kSmemBytes) != cudaSuccess) {
+        cudaGetLastError();
+        return MJXB_ECUDA;
+      }
+      attr_set[devid] = true;
     }
-    attr_set = true;
   }
   mjxbp::PolicyArgs P;
   P.n_env = n_env; P.obs_dim = obs_dim; P.act_dim = act_dim; P.obs = obs; P.rms_mean = rms_mean; P.rms_var = rms_var;

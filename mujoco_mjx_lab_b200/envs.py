@@ -45,7 +45,7 @@ def create_env_functions(sys: Model, cfg, q0, nq: int, nv: int) -> Tuple[Callabl
     if not np.array_equal(q0, np.asarray(sys.model["qpos0"], dtype=np.float32)):
         raise ValueError("q0 must be the model's qpos0 (reference src/training_utils.py:107)")
     env_sys = sys.with_env(make_env_config_c(cfg, nq, nv, sys.nu))
-    L = _lib.lib()
+    L = env_sys.lib
     dev, nu, od = env_sys.device, env_sys.nu, env_sys.obs_dim
     f32 = dict(dtype=torch.float32, device=dev)
 

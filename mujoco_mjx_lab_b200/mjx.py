@@ -34,7 +34,10 @@ class _Opt:
 class Model:
     """Stands in for `mjx.Model` (`sys` in the reference): compiled constants + a device-resident C handle."""
 
-    def __init__(self, model: Dict[str, Any], device: Optional[torch.device] = None, env_cfg_c: Optional[EnvConfigC] = None):
+    def __init__(self, model: Dict[str, Any], device: Optional[torch.device] = None, env_cfg_c: Optional[EnvConfigC] = None,
+                 variant: str = "fast", flags: Optional[int] = None):
+        """variant: "fast" (libmjxb.so, the product) or "exact" (libmjxb_exact.so, the reference-arithmetic yardstick of the parity tests);
+        flags: MJXB_FLAG_* bits for mjxb_model_create_ex (None: mjxb_model_create's defaults)."""
         if not torch.cuda.is_available():
             raise _lib.MjxbError("mujoco_mjx_lab_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.model = model
@@ -45,28 +48,38 @@ class Model:
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.qpos0 = torch.tensor(np.asarray(model["qpos0"], dtype=np.float32), device=self.device)
         self.env_cfg_c = env_cfg_c
-        L = _lib.lib()
+        self.variant, self.flags = variant, flags
+        L = self.lib = _lib.lib(variant)
         if L.mjxb_blob_sizeof() != self.blob.nbytes or L.mjxb_env_config_sizeof() != C.sizeof(EnvConfigC):
             raise _lib.MjxbError("ABI struct size mismatch between python and libmjxb.so")
         h = C.c_void_p()
         cfg_p = C.byref(env_cfg_c) if env_cfg_c is not None else None
-        _lib.check(L.mjxb_model_create(self.blob.ctypes.data_as(C.c_void_p), self.blob.nbytes, cfg_p, self.device.index or 0,
-                                       C.byref(h)), "mjxb_model_create")
+        if flags is None:
+            _lib.check(L.mjxb_model_create(self.blob.ctypes.data_as(C.c_void_p), self.blob.nbytes, cfg_p, self.device.index or 0,
+                                           C.byref(h)), "mjxb_model_create", L)
+        else:
+            _lib.check(L.mjxb_model_create_ex(self.blob.ctypes.data_as(C.c_void_p), self.blob.nbytes, cfg_p, self.device.index or 0,
+                                              int(flags), C.byref(h)), "mjxb_model_create_ex", L)
         self.handle = h
         self.obs_dim = 1 + 3 + (self.nq - 7) + self.nv + 2
 
     def with_env(self, env_cfg_c: EnvConfigC) -> "Model":
-        return Model(self.model, self.device, env_cfg_c)
+        return Model(self.model, self.device, env_cfg_c, self.variant, self.flags)
+
+    def reserve(self, n_env: int, stream: Optional[torch.cuda.Stream] = None):
+        """Pre-size the launch scratch of `stream` (default: the current one) -- required before capturing it into a CUDA graph."""
+        st = stream if stream is not None else torch.cuda.current_stream()
+        _lib.check(self.lib.mjxb_model_reserve(self.handle, int(n_env), C.c_void_p(st.cuda_stream)), "mjxb_model_reserve", self.lib)
 
     def launch_config(self):
         out = (C.c_int32 * 4)()
-        _lib.check(_lib.lib().mjxb_launch_config(self.handle, out))
+        _lib.check(self.lib.mjxb_launch_config(self.handle, out))
         return dict(warps_per_cta=out[0], smem_bytes=out[1], num_sms=out[2], warp_smem_bytes=out[3])
 
     def __del__(self):
         try:
             if getattr(self, "handle", None):
-                _lib.lib().mjxb_model_destroy(self.handle)
+                self.lib.mjxb_model_destroy(self.handle)
                 self.handle = None
         except Exception:
             pass
@@ -89,8 +102,8 @@ class Data:
                     None if self.ctrl is None else self.ctrl.clone())
 
 
-def put_model(model: Dict[str, Any], device=None) -> Model:
-    return Model(model, device)
+def put_model(model: Dict[str, Any], device=None, variant: str = "fast", flags: Optional[int] = None) -> Model:
+    return Model(model, device, None, variant, flags)
 
 
 def make_data(sys: Model, n: int = 1) -> Data:
@@ -142,7 +155,7 @@ def _physics(sys: Model, d: Data, nsteps: int, integrate: bool, debug: bool):
     ctrl = None if d.ctrl is None else _f32(d.ctrl, (n, sys.nu))
     status = torch.zeros(n, dtype=torch.int32, device=sys.device)
     dbg, out = _debug_buffers(sys, n) if debug else (None, {})
-    L = _lib.lib()
+    L = sys.lib
     st = state_c(qpos, qvel, warm, time)
     cp = C.c_void_p(ctrl.data_ptr()) if ctrl is not None else None
     dp = C.byref(dbg) if dbg is not None else None
@@ -172,5 +185,5 @@ def speed_test(sys: Model, vel: torch.Tensor, iters: int = 1) -> torch.Tensor:
     vel = _f32(vel, (vel.shape[0],))
     pos = torch.empty_like(vel)
     with torch.cuda.device(sys.device):
-        _lib.check(_lib.lib().mjxb_speed_test(sys.handle, vel.shape[0], vel.data_ptr(), pos.data_ptr(), iters, _stream()), "mjxb_speed_test")
+        _lib.check(sys.lib.mjxb_speed_test(sys.handle, vel.shape[0], vel.data_ptr(), pos.data_ptr(), iters, _stream()), "mjxb_speed_test")
     return pos

@@ -14,6 +14,8 @@ stores) and replayed per iteration: the host is out of the T-loop.
 """
 from __future__ import annotations
 
+import os
+
 import math
 import time
 from dataclasses import dataclass
@@ -102,21 +104,30 @@ class RMS:  # reference src/training_utils.py:20-56
         return cls(torch.zeros(dim, device=device), torch.ones(dim, device=device), torch.tensor(1e-4, device=device))
 
     def update(self, x: torch.Tensor, world: int):
-        """Welford merge of the batch moments; with sharded envs the batch moments are all-reduced first."""
-        n = torch.tensor(float(x.shape[0]), device=x.device)
-        s1, s2 = x.sum(0), (x * x).sum(0)
+        """reference src/training_utils.py:33-52 (update_rms): Chan merge of the batch moments into the running ones, variance floored at
+        1e-4. The batch moments are centred and accumulated in float64 (a one-pass E[x^2]-E[x]^2 in float32 cancels catastrophically on a
+        near-constant observation and can go negative); with sharded envs the per-rank (n, mean, M2) are Chan-merged across ranks through
+        one all-reduce of (n, n*mean, M2 + n*mean^2) in float64."""
+        xd = x.double()
+        n = torch.tensor(float(x.shape[0]), device=x.device, dtype=torch.float64)
+        b_mean = xd.mean(0)
+        m2 = ((xd - b_mean) ** 2).sum(0)
         if world > 1:
-            packed = torch.cat([s1, s2, n.reshape(1)])
+            packed = torch.cat([b_mean * n, m2 + n * b_mean * b_mean, n.reshape(1)])
             dist.all_reduce(packed)
-            s1, s2, n = packed[: x.shape[1]], packed[x.shape[1]: 2 * x.shape[1]], packed[-1]
-        b_mean = s1 / n
-        b_var = s2 / n - b_mean * b_mean
-        delta = b_mean - self.mean
-        tot = self.count + n
-        self.mean = self.mean + delta * n / tot
-        m_a, m_b = self.var * self.count, b_var * n
-        self.var = (m_a + m_b + delta * delta * self.count * n / tot) / tot
-        self.count = tot
+            d = x.shape[1]
+            n = packed[-1]
+            b_mean = packed[:d] / n
+            m2 = torch.clamp_min(packed[d: 2 * d] - n * b_mean * b_mean, 0.0)
+        b_var = m2 / n
+        mean, var, count = self.mean.double(), self.var.double(), self.count.double()
+        delta = b_mean - mean
+        tot = count + n
+        new_mean = mean + delta * n / tot
+        new_var = (var * count + b_var * n + delta * delta * count * n / tot) / tot
+        self.mean = new_mean.float()
+        self.var = torch.clamp_min(new_var, 1e-4).float()      # reference: new_var = max(new_var, 1e-4)
+        self.count = tot.float()
 
     def normalize(self, x):
         return torch.clamp((x - self.mean) / torch.sqrt(self.var + 1e-8), -10.0, 10.0)
@@ -203,8 +214,9 @@ class PPOTrainer:
             return
         if self.graph is None:
             # warm-up outside capture (allocator pools, lazy library state, the overflow list), then capture the whole T-loop
-            s = torch.cuda.Stream(device=self.dev)
+            s = self.cap_stream = torch.cuda.Stream(device=self.dev)
             s.wait_stream(torch.cuda.current_stream())
+            self.sys.reserve(self.n, s)                                 # the step's launch scratch is per stream: size it before capturing
             with torch.cuda.stream(s):
                 saved = [t.clone() for t in (self.state[0].qpos, self.state[0].qvel, self.state[0].qacc_warmstart, self.state[0].time,
                                              self.state[1], self.obs)]
@@ -219,12 +231,20 @@ class PPOTrainer:
             self.rms_mean_buf, self.rms_var_buf = self.rms.mean.clone(), self.rms.var.clone()
             graph_rms = RMS(self.rms_mean_buf, self.rms_var_buf, self.rms.count)
             real_rms, self.rms = self.rms, graph_rms
-            with torch.cuda.graph(self.graph):
+            with torch.cuda.graph(self.graph, stream=s):             # capture on the stream whose scratch was reserved
                 self._rollout_body()
             self.rms = real_rms
         self.rms_mean_buf.copy_(self.rms.mean)
         self.rms_var_buf.copy_(self.rms.var)
         self.graph.replay()
+
+    def check_health(self):
+        """Once per rollout (one host sync): a tensor-core completion that was never observed by the fused policy kernel, or non-finite
+        rewards / observations from the step, must stop training instead of being learned from."""
+        if self.fused is not None and int(self.fused.error) != 0:
+            raise RuntimeError("fused policy kernel reported a tensor-core completion timeout")
+        if not (bool(torch.isfinite(self.r_traj).all()) and bool(torch.isfinite(self.obs).all())):
+            raise RuntimeError("non-finite reward / observation in the rollout (MJXB_STATUS_NAN)")
 
     # ---------------------------------------------------------------- GAE (train_ppo.py:171-202)
     @torch.no_grad()
@@ -268,33 +288,57 @@ class PPOTrainer:
         loss_v.backward()
 
     def _capture_update(self):
-        """Graph 1: gather + forward + backward (+ Adam when single-GPU, else + flatten of the gradients); graph 2 (sharded runs
-        only, replayed after the eager NCCL all-reduce of the flat gradient): averaged gradients back + Adam."""
+        """One CUDA graph per minibatch step: gather + forward + backward + (sharded runs) the NCCL all-reduce of the flat gradient,
+        captured INSIDE the graph, + Adam. A minibatch is then a single replay with no host round trip between the backward pass and
+        the optimiser (the eager all-reduce wedged between two replays cost ~185 us per minibatch at 8 GPUs, profiles/r1_bench_n8.json).
+        If this NCCL build refuses stream capture the collective stays eager between two graphs (u["st"] is then the second half)."""
         u = self.upd
         params = self.policy + [self.log_std] + self.value
         torch.cuda.synchronize()
-        self.opt_p.zero_grad(set_to_none=True)
-        self.opt_v.zero_grad(set_to_none=True)
-        u["fb"] = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(u["fb"]):
-            self._minibatch_fb(u["obs"], u["act"], u["logp"], u["ret"], u["adv"], u["idx"], zero=False)
-            if self.world == 1:
-                self.opt_p.step()
-                self.opt_v.step()
-            else:
-                u["flat"].copy_(torch.cat([p.grad.reshape(-1) for p in params]))
-        if self.world > 1:
-            u["st"] = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(u["st"], pool=u["fb"].pool()):
-                o = 0
-                for p in params:
-                    p.grad.copy_(u["flat"][o:o + p.numel()].view_as(p.grad) / self.world)
-                    o += p.numel()
-                self.opt_p.step()
-                self.opt_v.step()
+
+        def unflatten_and_step():
+            o = 0
+            for p in params:
+                p.grad.copy_(u["flat"][o:o + p.numel()].view_as(p.grad) / self.world)
+                o += p.numel()
+            self.opt_p.step()
+            self.opt_v.step()
+
+        def capture(fused_collective: bool):
+            self.opt_p.zero_grad(set_to_none=True)
+            self.opt_v.zero_grad(set_to_none=True)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._minibatch_fb(u["obs"], u["act"], u["logp"], u["ret"], u["adv"], u["idx"], zero=False)
+                if self.world == 1:
+                    self.opt_p.step()
+                    self.opt_v.step()
+                else:
+                    u["flat"].copy_(torch.cat([p.grad.reshape(-1) for p in params]))
+                    if fused_collective:
+                        dist.all_reduce(u["flat"])
+                        unflatten_and_step()
+            return g
+
+        u["st"] = None
+        fused = self.world > 1 and os.environ.get("MJXB_PPO_EAGER_ALLREDUCE") is None
+        if fused:
+            try:
+                u["fb"] = capture(True)
+            except Exception as e:                                      # capture of the collective unsupported: keep it eager
+                print(f"[ppo] NCCL all-reduce could not be captured ({type(e).__name__}: {e}); using an eager all-reduce between two graphs")
+                torch.cuda.synchronize()
+                fused = False
+        if not fused:
+            u["fb"] = capture(False)
+            if self.world > 1:
+                u["st"] = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(u["st"], pool=u["fb"].pool()):
+                    unflatten_and_step()
+        u["collective_in_graph"] = bool(fused)
         # capture does not execute: run this minibatch now
         u["fb"].replay()
-        if self.world > 1:
+        if u["st"] is not None:
             dist.all_reduce(u["flat"])
             u["st"].replay()
 
@@ -361,15 +405,17 @@ class PPOTrainer:
                     self._capture_update()      # captures, then runs this minibatch
                     continue
                 u["fb"].replay()
-                if self.world > 1:
+                if u["st"] is not None:
                     dist.all_reduce(u["flat"])
                     u["st"].replay()
         ev[2].record()
         torch.cuda.synchronize()
+        self.check_health()                                             # after the timed region: the iteration already synchronised
         done = torch.maximum(self.term_traj, self.trunc_traj).sum()
         out = {"rollout_ms": ev[0].elapsed_time(ev[1]), "update_ms": ev[1].elapsed_time(ev[2]), "iter_ms": ev[0].elapsed_time(ev[2]),
                "train_return_avg": float(self.r_traj.sum(0).mean()), "train_eplen_avg": float(total / max(float(done), 1.0)),
-               "minibatches": cfg.epochs * steps_per_epoch, "allreduce_floats": self.n_grads if self.world > 1 else 0}
+               "minibatches": cfg.epochs * steps_per_epoch, "allreduce_floats": self.n_grads if self.world > 1 else 0,
+               "collective_in_graph": bool(self.upd and self.upd.get("collective_in_graph"))}
         return out
 
 
@@ -404,6 +450,6 @@ def time_ppo(num_envs_local: int, rollout_length: int, iters: int = 5, warmup: i
     res = {k: parallel.max_over_ranks(v / iters, tr.dev) for k, v in acc.items()}
     res.update(wall_iter_ms=wall, envs_per_gpu=num_envs_local, rollout_length=rollout_length, world=tr.world,
                env_steps_per_sec=num_envs_local * tr.world * rollout_length / (wall * 1e-3), minibatches=last.get("minibatches"),
-               allreduce_floats_per_minibatch=last.get("allreduce_floats"), train_return_avg=last.get("train_return_avg"),
+               allreduce_floats_per_minibatch=last.get("allreduce_floats"), collective_in_graph=last.get("collective_in_graph"), train_return_avg=last.get("train_return_avg"),
                cuda_graph=bool(use_cuda_graph), fused_policy_kernel=tr.fused is not None)
     return res

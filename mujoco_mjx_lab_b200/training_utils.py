@@ -10,7 +10,8 @@ from .envs import create_env_functions
 
 
 def load_model_and_create_env(xml_path: str, env_config: Any, lighten_solver: bool = False,
-                              solver_options: Optional[Dict[str, Any]] = None, model: Optional[Dict[str, Any]] = None):
+                              solver_options: Optional[Dict[str, Any]] = None, model: Optional[Dict[str, Any]] = None,
+                              variant: str = "fast", flags: Optional[int] = None):
     """Returns (m, sys, q0, nq, nv, nu, single_reset, single_step, v_reset, v_step) like the reference.
 
     `m` is the compiled-constants dict (stands in for mujoco.MjModel), `sys` the device model (stands in for mjx.Model).
@@ -31,7 +32,7 @@ def load_model_and_create_env(xml_path: str, env_config: Any, lighten_solver: bo
     env_config.head_body_id = m["body_name"].index("head")
     env_config.touch_sensor_right_id = m["sensor_name"].index("touch_foot_right")
     env_config.touch_sensor_left_id = m["sensor_name"].index("touch_foot_left")
-    sys = mjx.put_model(m)
+    sys = mjx.put_model(m, variant=variant, flags=flags)   # variant / flags: test-only knobs (mjx.Model)
     nq, nv, nu = int(m["nq"]), int(m["nv"]), int(m["nu"])
     q0 = np.asarray(m["qpos0"], dtype=np.float32).copy()
     single_reset, single_step, v_reset, v_step = create_env_functions(sys, env_config, q0, nq, nv)

@@ -129,6 +129,9 @@ template <class R> struct Data {
   R sensordata[MJXB_MAXSENSOR];
   int solver_niter;
   long flops;  // counted multiply/add operations of the dense formulation (SURVEY.md 8d counting model)
+  // the same step counted activity-aware (SURVEY.md 8d "activity-aware minimum"): only candidate rows are assembled, only rows active at
+  // the current iterate enter J^T D J (756 = 2 * 27*28/2 flops per active row), tree-sparse factor_m; counting rules in DESIGN.md
+  long flops_act;
 };
 
 // ---------------------------------------------------------------- dense Cholesky (jax.scipy.linalg.cho_factor/cho_solve)
@@ -688,6 +691,11 @@ template <class R> void update_gradient(const mjxb_model_blob& m, Data<R>& d, So
   chol_factor(L, H, m.nv);
   chol_solve(c.Mgrad, L, c.grad, m.nv);
   d.flops += 2L * m.nefc * m.nv * (m.nv + 1) / 2 + 6600 + 1500;
+  {  // activity-aware: J^T D J over the rows active at this iterate + factor/solve + the iteration's matvecs and line search (20K)
+    long nact = 0;
+    for (int r = 0; r < m.nefc; r++) nact += c.active[r] ? 1 : 0;
+    d.flops_act += 756L * nact + 20000L;
+  }
 }
 template <class R> void ctx_create(const mjxb_model_blob& m, Data<R>& d, SolverCtx<R>& c, const R* qacc, bool grad) {
   for (int j = 0; j < m.nv; j++) c.qacc[j] = qacc[j];
@@ -904,6 +912,12 @@ template <class R> void forward(const mjxb_model_blob& m, Data<R>& d) {
   fwd_acceleration(m, d);
   solve(m, d);
   sensor_touch(m, d);
+  {  // activity-aware fixed part: kinematics 4K, com/cinert/cdof 3K, crb 3K, tree-sparse factor_m 2.6K + solve 0.5K, 108 pair tests 13K,
+     // rows of the candidates only (27*12+60 each) + their J*qvel (54 each), com_vel/rne 6K, sensor/obs/reward 1K, implicit integrate 3K
+    long ncand = 0;
+    for (int r = 0; r < m.nefc; r++) ncand += d.efc_cand[r] ? 1 : 0;
+    d.flops_act += 4000 + 3000 + 3000 + 3100 + 13000 + ncand * (27 * 12 + 60 + 54) + 6000 + 1000 + 3000;
+  }
 }
 template <class R> void integrate(const mjxb_model_blob& m, Data<R>& d) {
   // implicitfast (qDeriv = -diag(damping)) and Euler with eulerdamp solve the same system for this model family

@@ -17,8 +17,8 @@ _LIB_PATH = os.path.join(_HERE, "liboracle.so")
 
 _DBG_FIELDS = ("xpos", "xquat", "qM", "qfrc_bias", "qfrc_passive", "qfrc_actuator", "qacc_smooth", "con_dist", "con_pos",
                "con_normal", "efc_J", "efc_pos", "efc_D", "efc_aref", "efc_force", "efc_active", "qacc", "qfrc_constraint",
-               "sensordata", "solver_niter", "flops", "cdof", "cinert", "subtree_com", "qfrc_smooth")
-_DBG_INT = {"efc_active": np.int32, "solver_niter": np.int32, "flops": np.int64}
+               "sensordata", "solver_niter", "flops", "cdof", "cinert", "subtree_com", "qfrc_smooth", "flops_act")
+_DBG_INT = {"efc_active": np.int32, "solver_niter": np.int32, "flops": np.int64, "flops_act": np.int64}
 
 
 class _DebugC(C.Structure):
@@ -78,7 +78,7 @@ class Oracle:
                       efc_pos=(n, self.nefc), efc_D=(n, self.nefc), efc_aref=(n, self.nefc), efc_force=(n, self.nefc),
                       efc_active=(n, self.nefc), qacc=(n, self.nv), qfrc_constraint=(n, self.nv),
                       sensordata=(n, self.nsensor), solver_niter=(n,), flops=(n,), cdof=(n, self.nv, 6),
-                      cinert=(n, self.nbody, 10), subtree_com=(n, self.nbody, 3), qfrc_smooth=(n, self.nv))
+                      cinert=(n, self.nbody, 10), subtree_com=(n, self.nbody, 3), qfrc_smooth=(n, self.nv), flops_act=(n,))
         names = _DBG_FIELDS if want is True else want
         out, dbg = {}, _DebugC()
         for name in names:

@@ -17,6 +17,7 @@ typedef struct orc_debug {
   double* efc_D; double* efc_aref; double* efc_force; int32_t* efc_active; double* qacc; double* qfrc_constraint;
   double* sensordata; int32_t* solver_niter; int64_t* flops;
   double* cdof; double* cinert; double* subtree_com; double* qfrc_smooth;
+  int64_t* flops_act;
 } orc_debug;
 
 size_t orc_blob_sizeof(void) { return sizeof(mjxb_model_blob); }
@@ -85,6 +86,7 @@ template <class R> void store_debug(const mjxb_model_blob& m, const Data<R>& d, 
   if (g->sensordata) for (int s = 0; s < m.nsensor; s++) g->sensordata[(size_t)e * m.nsensor + s] = d.sensordata[s];
   if (g->solver_niter) g->solver_niter[e] = d.solver_niter;
   if (g->flops) g->flops[e] = d.flops;
+  if (g->flops_act) g->flops_act[e] = d.flops_act;
 }
 
 template <class R>
@@ -98,7 +100,7 @@ void physics_step_t(const mjxb_model_blob& m, int n, int nsteps, int do_integrat
     for (int e = 0; e < n; e++) {
       load_state(m, d, e, qpos, qvel, warm, time, ctrl);
       for (int s = 0; s < nsteps; s++) {
-        d.flops = 0;
+        d.flops = 0; d.flops_act = 0;
         forward(m, d);
         if (s == nsteps - 1) store_debug(m, d, e, dbg);
         if (do_integrate) integrate(m, d);
@@ -141,7 +143,7 @@ void env_step_t(const mjxb_model_blob& m, const mjxb_env_config& cfg, int n, dou
       for (int k = 0; k < MJXB_AUX_DIM; k++) a[k] = R(aux[(size_t)e * MJXB_AUX_DIM + k]);
       for (int k = 0; k < m.nu; k++) act[k] = R(action[(size_t)e * m.nu + k]);
       EnvOut<R> out;
-      d.flops = 0;
+      d.flops = 0; d.flops_act = 0;
       env_step(m, cfg, d, a, act, out);
       store_debug(m, d, e, dbg);
       reward[e] = double(out.reward); terminated[e] = double(out.terminated); truncated[e] = double(out.truncated);
@@ -181,6 +183,63 @@ template <class R> void speed_test_t(const mjxb_model_blob& m, int n, const doub
 extern "C" {
 
 int orc_max_threads(void) { return omp_get_max_threads(); }
+
+// mj_setConst quantities at qpos0 (engine_setconst.c: dof_invweight0, body_invweight0, tendon_invweight0, stat.meaninertia), derived
+// here from the oracle's OWN pipeline -- kinematics -> com_pos -> crb mass matrix -> Cholesky -> M^-1, body Jacobians from cdof -- i.e.
+// independently of modelc.py's per-body point-Jacobian construction that produced the values stored in the blob. Float64 throughout.
+void orc_set_const(const mjxb_model_blob* mp, double* dof_invweight0, double* body_invweight0 /*[nbody,2]*/, double* tendon_invweight0,
+                   double* meaninertia) {
+  const mjxb_model_blob& m = *mp;
+  std::unique_ptr<Data<double>> dp(new Data<double>());
+  Data<double>& d = *dp;
+  for (int i = 0; i < m.nq; i++) d.qpos[i] = double(m.qpos0[i]);
+  for (int i = 0; i < m.nv; i++) d.qvel[i] = 0;
+  kinematics(m, d);
+  com_pos(m, d);
+  crb(m, d);
+  chol_factor(d.qL, d.qM, m.nv);
+  static double Minv[MJXB_MAXDOF][MJXB_MAXDOF];
+  for (int j = 0; j < m.nv; j++) {
+    double e[MJXB_MAXDOF] = {0}, x[MJXB_MAXDOF];
+    e[j] = 1;
+    chol_solve(x, d.qL, e, m.nv);
+    for (int i = 0; i < m.nv; i++) Minv[i][j] = x[i];
+  }
+  double tr = 0;
+  for (int i = 0; i < m.nv; i++) { dof_invweight0[i] = Minv[i][i]; tr += d.qM[i][i]; }
+  *meaninertia = tr / m.nv;
+  for (int j = 0; j < m.njnt; j++)
+    if (m.jnt_type[j] == 0) {  // free joint: translational and rotational dofs share their mean
+      int a = m.jnt_dofadr[j];
+      double t = (Minv[a][a] + Minv[a + 1][a + 1] + Minv[a + 2][a + 2]) / 3, r = (Minv[a + 3][a + 3] + Minv[a + 4][a + 4] + Minv[a + 5][a + 5]) / 3;
+      for (int k = 0; k < 3; k++) { dof_invweight0[a + k] = t; dof_invweight0[a + 3 + k] = r; }
+    }
+  for (int b = 0; b < m.nbody; b++) {
+    body_invweight0[2 * b] = body_invweight0[2 * b + 1] = 0;
+    if (b == 0) continue;
+    double jp[MJXB_MAXDOF][3], jr[MJXB_MAXDOF][3];
+    point_jac(m, d, jp, d.xipos[b], b);   // translational Jacobian of the body's inertial-frame origin (mjx support.jac)
+    for (int j = 0; j < m.nv; j++) jr[j][0] = jr[j][1] = jr[j][2] = 0;
+    int bb = b;
+    while (bb > 0 && m.body_dofnum[bb] == 0) bb = m.body_parent[bb];
+    if (bb > 0)
+      for (int j = m.body_dofadr[bb] + m.body_dofnum[bb] - 1; j >= 0; j = m.dof_parent[j])
+        for (int k = 0; k < 3; k++) jr[j][k] = d.cdof[j][k];   // angular part of cdof = world rotation axis of the dof
+    double tp = 0, trr = 0;
+    for (int k = 0; k < 3; k++)
+      for (int i = 0; i < m.nv; i++)
+        for (int j = 0; j < m.nv; j++) { tp += jp[i][k] * Minv[i][j] * jp[j][k]; trr += jr[i][k] * Minv[i][j] * jr[j][k]; }
+    body_invweight0[2 * b] = std::max(MINVAL, tp / 3);
+    body_invweight0[2 * b + 1] = std::max(MINVAL, trr / 3);
+  }
+  for (int t = 0; t < m.ntendon; t++) {
+    double jt[MJXB_MAXDOF] = {0}, s = 0;
+    for (int w = 0; w < m.ten_nwrap[t]; w++) jt[m.ten_dof[t][w]] += double(m.ten_coef[t][w]);
+    for (int i = 0; i < m.nv; i++)
+      for (int j = 0; j < m.nv; j++) s += jt[i] * Minv[i][j] * jt[j];
+    tendon_invweight0[t] = s;
+  }
+}
 
 void orc_physics_step(const mjxb_model_blob* m, int prec, int n, int nsteps, int do_integrate, double* qpos, double* qvel,
                       double* warm, double* time, const double* ctrl, const orc_debug* dbg, int nthreads) {
