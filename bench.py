@@ -34,12 +34,20 @@ sys.path.insert(0, ROOT)
 METRIC = "humanoid_env_steps_per_sec"
 UNIT = "env-steps/s"
 ALG_BYTES_PER_STEP = 1056          # state r/w 2*368 + action 84 + obs/reward/done 228 + key 8
-FP32_PEAK_TFLOPS = 74.4            # 148 SM x 128 lanes x 2 x 1.965 GHz (nominal)
+FP32_NOMINAL_TFLOPS = 74.4         # 148 SM x 128 lanes x 2 x 1.965 GHz (nominal; the line reports the MEASURED FFMA peak beside it)
 
 
-def algorithmic_flops(mean_newton_iters: float, mean_rows: float) -> float:
-    """Activity-aware counting model of SURVEY.md 8d: F = 70K + n_newton * (756 * n_act + 20K)."""
-    return 70e3 + mean_newton_iters * (756.0 * mean_rows + 20e3)
+def counted_flops(oracle, qpos, qvel, warm, ctrl):
+    """Algorithmic FLOPs per env-step COUNTED by the CPU oracle's stage counters on a sample of the measured state distribution
+    (oracle/oracle.hpp: `flops` = the dense formulation MJX executes, `flops_act` = the activity-aware minimum of SURVEY.md 8d:
+    candidate rows only, rows active at each Newton iterate in J^T D J, tree-sparse factor_m; counting rules in DESIGN.md)."""
+    out = oracle.physics_step(qpos, qvel, warm, None, ctrl, prec="f32", integrate=False,
+                              debug=("flops", "flops_act", "solver_niter", "efc_active"))
+    act = (out["efc_active"] >> 1).sum(1)
+    cand = (out["efc_active"] & 1).sum(1)
+    return dict(flops_per_env_step=float(out["flops_act"].mean()), flops_per_env_step_dense=float(out["flops"].mean()),
+                mean_newton_iters=float(out["solver_niter"].mean()), mean_candidate_rows=float(cand.mean()),
+                mean_active_rows=float(act.mean()), sample_envs=int(qpos.shape[0]))
 
 
 class ClockSampler(threading.Thread):
@@ -112,7 +120,10 @@ def main():
     ap.add_argument("--cpu-sample-envs", type=int, default=8192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ppo", action="store_true")
-    ap.add_argument("--ppo-large", action="store_true", help="also time config 5 (65536 envs/GPU PPO iteration)")
+    ap.add_argument("--ppo-large", action="store_true", help="(default now) also time config 5 (65536 envs/GPU PPO iteration)")
+    ap.add_argument("--no-ppo-large", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--no-apg", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank, local_rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -127,6 +138,10 @@ def main():
         n = min(args.cpu_sample_envs, args.envs)
         steps = max(1, min(args.steps, 8))
         val, dt, threads = cpu_reference_run(n, steps, min(args.warmup, 3))
+        config = dict(config, envs_per_gpu=n, steps_timed=steps,
+                      workload=f"humanoid_mjx v_step+auto-reset, BOUNDED SAMPLE of the bench workload: {n} envs x {steps} steps on {threads} host "
+                               f"threads (the GPU arm runs {args.envs} envs/GPU), trajectory distribution B",
+                      l2="n/a (CPU)", parallelism=f"OpenMP over envs, {threads} threads")
         line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 3),
                 "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": config,
@@ -170,10 +185,13 @@ def main():
     parallel.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    L = _lib.lib()
+    launches_0, launch_calls = L.mjxb_launch_count(), args.steps
     e0.record()
     for i in range(args.steps):
         state, obs, r, te, tr = v_step.autoreset(state, acts[i % nbuf], keys[i % nbuf], inplace=True)
     e1.record()
+    gpu_launches = int(L.mjxb_launch_count() - launches_0)
     torch.cuda.synchronize()
     parallel.barrier()
     ms_total = parallel.max_over_ranks(e0.elapsed_time(e1), dev)
@@ -185,7 +203,7 @@ def main():
     done_frac = float(torch.maximum(te, tr).mean())
 
     # ---- end to end through the host-buffer ABI call (pinned host buffers; H2D + kernel + D2H timed)
-    L, h = _lib.lib(), env_sys.handle
+    h = env_sys.handle
     pin = lambda *s, dt=torch.float32: torch.empty(*s, dtype=dt, pin_memory=True)
     h_act = [pin(n, nu) for _ in range(nbuf)]                        # the same action / key sequence as the device-resident leg
     h_keys = [pin(n, 2, dt=torch.int32) for _ in range(nbuf)]
@@ -212,25 +230,47 @@ def main():
     e2e_value = n * world * e2e_steps / e2e_s
     h2d, d2h = n * (nu * 4 + 8), n * (env_sys.obs_dim + 3) * 4
 
-    # ---- solver statistics of the measured distribution (feeds the FLOP counting model) -- untimed
+    # ---- solver statistics of the measured distribution (GPU, untimed) and a sample of it for the oracle's FLOP counters
     nstat = min(n, 65536)
     dd = mjx.Data(d.qpos[:nstat], d.qvel[:nstat], d.qacc_warmstart[:nstat], d.time[:nstat], acts[0][:nstat])
     _, dbg = mjx.forward(env_sys, dd, debug=True)
     mean_iters = float(dbg["solver_niter"].float().mean())
     mean_rows = float((dbg["efc_active"] & 1).sum(1).float().mean())
+    mean_active = float((dbg["efc_active"] >> 1).sum(1).float().mean())
     spill_frac = float(((dbg["status"] & 2) != 0).float().mean())
-    flops = algorithmic_flops(mean_iters, mean_rows)
+    nflop = min(n, 4096)
+    flop_sample = [t[:nflop].double().cpu().numpy() for t in (d.qpos, d.qvel, d.qacc_warmstart, acts[0])]
+
+    # ---- FP32 FMA-pipe ceiling of this GPU, measured (FFMA-saturating microbenchmark inside libmjxb.so)
+    import ctypes as C
+    ffma_tf, ffma_ms = C.c_float(0), C.c_float(0)
+    _lib.check(L.mjxb_ffma_peak(local_rank, C.byref(ffma_tf), C.byref(ffma_ms)), "mjxb_ffma_peak")
+
+    # ---- BASELINE configs[0..1]: the small batches the reference itself runs (64 = its CPU case, 4096 = mjx_humanoid_speed_test.py:141,
+    # 1024 = its PPO batch), both input distributions of SURVEY.md 8d, on this rank's GPU
+    sweep = []
+    if not args.no_sweep:
+        del state, obs
+        for ns in (64, 1024, 4096):
+            sweep.append(sweep_point(ns, v_reset, v_step, env_sys, nu, dev))
 
     # ---- PPO iteration time (the second half of BASELINE.json's metric): the caller of the hot path, reference train_ppo.py
     ppo = {}
     if not args.no_ppo:
         from mujoco_mjx_lab_b200 import ppo as ppo_mod
-        del acts, keys, state, obs
+        del acts, keys
         torch.cuda.empty_cache()
         n3 = max(1024 // world, 16)                                  # config 3: 1024 envs total x 256 steps, sharded
         ppo["config3"] = ppo_mod.time_ppo(n3, 256, iters=5, warmup=3, minibatch_size=65536, model=model)
-        if args.ppo_large:                                           # config 5: 65536 envs per GPU, NCCL gradient all-reduce
+        if not args.no_ppo_large:                                    # config 5: 65536 envs per GPU, NCCL gradient all-reduce
             ppo["config5"] = ppo_mod.time_ppo(65536, 256, iters=2, warmup=1, minibatch_size=65536, model=model)
+    apg = {}
+    if not args.no_apg:                                              # config 4: APG 2048 envs x 128 horizon, CG 4/4, reverse-mode step kernels
+        try:
+            from mujoco_mjx_lab_b200 import apg as apg_mod
+            apg["config4"] = apg_mod.time_apg(max(2048 // world, 16), 128, iters=3, warmup=2)
+        except ImportError:
+            apg["config4"] = {"unavailable": "apg module not built"}
     if rank != 0:
         return
     peaks = {}
@@ -241,41 +281,136 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     traffic = None                                                # dram bytes per step launch from the committed ncu capture
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        tp = [q for q in (os.path.join(ROOT, "profiles", f) for f in ("r2_traffic.json", "r1_traffic.json")) if os.path.exists(q)]
+        tj = json.load(open(tp[0]))
         if int(tj["n_env"]) == n:
             traffic = float(tj["dram_bytes_per_launch"])
     except Exception:
         pass
-    kernel_ms = ms_step                                           # one step == one step-kernel launch (+ an empty overflow pass)
+    kernel_ms = ms_step                                           # one step == one step-kernel launch (+ two empty overflow passes)
     ach_gbs = ALG_BYTES_PER_STEP * n / (kernel_ms * 1e-3) / 1e9
-    ach_tflops = flops * n / (kernel_ms * 1e-3) / 1e12
+    ffma_peak = float(ffma_tf.value)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": config,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "api": "mjxb_step_autoreset_host (pinned host buffers; one launch, action/keys streamed in behind ready flags, outputs stored into the caller's mapped buffers)"},
-        "gpu_launches": 3 * args.steps,
+        "gpu_launches": gpu_launches,
+        "gpu_launches_note": "counted by libmjxb.so (mjxb_launch_count) over the timed region: per step the main tier + two overflow tiers that exit at once when their list is empty",
         "kernels": ["mjxb_step_kernel<false,32,16,16,true,true> (step: 32-row tile, 16 env-warps per SM, single-step instantiation)",
                     "mjxb_step_kernel<false,64,24,10,true,false> and <false,320,176,3,true,false> (overflow tiers; exit at once when their list is empty)"],
         "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                      "traffic": traffic, "algorithmic_bytes_per_launch": ALG_BYTES_PER_STEP * n, "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 (of fallback)",
                      "algorithmic_bytes_per_env_step": ALG_BYTES_PER_STEP, "kernel_ms": kernel_ms,
                      "note": "the step is FP32-pipe/latency bound, ~16x under its HBM ceiling; see roofline_fp32"},
-        "roofline_fp32": {"bound": "fp32 CUDA cores", "achieved": ach_tflops, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
-                          "frac": ach_tflops / FP32_PEAK_TFLOPS, "flops_per_env_step": flops, "mean_newton_iters": mean_iters,
-                          "mean_candidate_rows": mean_rows, "peak_source": "nominal 148 SM x 128 lanes x 2 x 1.965 GHz"},
-        "workload_stats": {"done_frac_per_step": done_frac, "overflow_rerun_frac": spill_frac},
+        "workload_stats": {"done_frac_per_step": done_frac, "overflow_rerun_frac": spill_frac, "mean_newton_iters_gpu": mean_iters,
+                           "mean_candidate_rows_gpu": mean_rows, "mean_active_rows_gpu": mean_active},
         "published_reference_steps_per_sec": 72618, "x_published_reference": value / world / 72618.0,
         "clocks": sampler.summary() if sampler else None,
+        "sweep": sweep,
         "ppo_iter": ppo,
+        "apg_iter": apg,
+        "arithmetic": "product build: --use_fast_math + closed-form exact line search where MJX iterates its own to convergence; both deviations "
+                      "from MJX's float32 arithmetic are quantified against the reference-arithmetic build in profiles/r2_parity.json",
     }
     if not args.no_cpu_baseline and world == 1:
         ncpu = min(args.cpu_sample_envs, n)
         val, dt, threads = cpu_reference_run(ncpu, 4, 1)
         line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": f"{ncpu} envs x 4 steps of the same workload, CPU oracle (float32 restatement of mjx.step + src/envs.py), {dt:.1f} s"}
+    # the two CPU baselines north_star names (MuJoCo C, MJX on JAX-CPU): self-reporting scripts, UNAVAILABLE in this image
+    if world == 1:
+        nsb = {}
+        for name in ("run_mujoco_c.py", "run_mjx_cpu.py"):
+            try:
+                out = subprocess.run([sys.executable, os.path.join(ROOT, "baseline", name)], capture_output=True, text=True, timeout=300).stdout.strip()
+                nsb[name] = json.loads(out.splitlines()[-1]) if out else {"status": "no output"}
+            except Exception as e:
+                nsb[name] = {"status": "error", "why": f"{type(e).__name__}: {e}"}
+        line["north_star_cpu_baselines"] = nsb
+    # FP32 roofline: FLOPs counted by the oracle's stage counters on a sample of the measured states (rank 0; the counting model's formula
+    # with the GPU's own statistics is kept beside it), against the MEASURED FFMA peak
+    fl = None
+    if not args.no_cpu_baseline:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import helpers
+            from oracle import oracle as O
+            O.build()
+            orc = helpers.make_oracle(model, helpers.env_config())
+            fl = counted_flops(orc, *flop_sample)
+        except Exception as e:                                      # the counters are a reporting aid: never fail the bench line on them
+            fl = {"error": f"{type(e).__name__}: {e}"}
+    formula = 70e3 + mean_iters * (756.0 * mean_active + 20e3)
+    flops = fl["flops_per_env_step"] if fl and "flops_per_env_step" in fl else formula
+    ach_tflops = flops * n / (kernel_ms * 1e-3) / 1e12
+    line["roofline_fp32"] = {"bound": "fp32 CUDA cores", "achieved": ach_tflops, "peak": ffma_peak, "unit": "TFLOP/s", "frac": ach_tflops / ffma_peak,
+                             "peak_source": f"measured: FFMA microbenchmark in libmjxb.so (mjxb_ffma_peak, {ffma_ms.value:.3f} ms best of 4) -- of measured",
+                             "peak_nominal": FP32_NOMINAL_TFLOPS, "frac_of_nominal": ach_tflops / FP32_NOMINAL_TFLOPS,
+                             "flops_per_env_step": flops, "flops_source": "oracle stage counters (activity-aware), sample of the measured states" if fl and "flops_per_env_step" in fl else "formula 70K + n_newton (756 n_active + 20K) with the GPU's statistics",
+                             "flops_formula_with_gpu_stats": formula, "counted": fl}
     print(json.dumps(line))
+
+
+def sweep_point(n, v_reset, v_step, env_sys, nu, dev):
+    """One batch size of BASELINE configs[0..1]: (A) speed-test semantics (cold steps in one launch, like the reference's fori_loop) and
+    (B) trajectory distribution with auto-reset -- timed both as the API is called (one launch triple per step from the host) and as a
+    trainer uses it (the steps replayed from a CUDA graph)."""
+    import torch
+    from mujoco_mjx_lab_b200 import mjx, parallel
+    rank = int(os.environ.get("RANK", "0"))
+    g = torch.Generator(device=dev).manual_seed(99 + rank)
+    state, obs = v_reset(torch.from_numpy(parallel.rank_keys(7, rank, n).view(np.int32)).to(dev))
+    acts = [torch.randn(n, nu, device=dev, generator=g).clamp_(-1, 1) for _ in range(4)]
+    rk = [torch.randint(-2 ** 31, 2 ** 31 - 1, (n, 2), device=dev, dtype=torch.int32, generator=g) for _ in range(4)]
+    for i in range(64):
+        state, obs, r, te, tr = v_step.autoreset(state, acts[i % 4], rk[i % 4], inplace=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    nt = 200
+    e0.record()
+    for i in range(nt):
+        state, obs, r, te, tr = v_step.autoreset(state, acts[i % 4], rk[i % 4], inplace=True)
+    e1.record()
+    torch.cuda.synchronize()
+    eager_ms = e0.elapsed_time(e1) / nt
+    G = 32
+    s = torch.cuda.Stream(device=dev)
+    s.wait_stream(torch.cuda.current_stream())
+    env_sys.reserve(n, s)
+    with torch.cuda.stream(s):
+        for i in range(4):
+            state, obs, r, te, tr = v_step.autoreset(state, acts[i % 4], rk[i % 4], inplace=True)
+    torch.cuda.current_stream().wait_stream(s)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=s):
+        for i in range(G):
+            state, obs, r, te, tr = v_step.autoreset(state, acts[i % 4], rk[i % 4], inplace=True)
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    reps = 8
+    e0.record()
+    for _ in range(reps):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    graph_ms = e0.elapsed_time(e1) / (reps * G)
+    vel = torch.linspace(0, 1, n, device=dev)
+    iters = 200
+    mjx.speed_test(env_sys, vel, 3)
+    torch.cuda.synchronize()
+    e0.record()
+    mjx.speed_test(env_sys, vel, iters)
+    e1.record()
+    torch.cuda.synchronize()
+    st_ms = e0.elapsed_time(e1) / iters
+    return dict(n_env=n, trajectory_graph_ms_per_step=graph_ms, trajectory_graph_steps_per_s=n / graph_ms * 1e3,
+                trajectory_eager_ms_per_step=eager_ms, trajectory_eager_steps_per_s=n / eager_ms * 1e3,
+                speedtest_ms_per_step=st_ms, speedtest_steps_per_s=n / st_ms * 1e3,
+                note="trajectory: v_step + fused auto-reset (distribution B); graph = 32 steps per CUDA-graph replay; speedtest: "
+                     "mjx_humanoid_speed_test.py semantics, 200 cold steps inside one launch (distribution A)")
 
 
 def _shutdown():

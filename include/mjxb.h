@@ -102,6 +102,8 @@ typedef struct mjxb_debug {
 typedef struct mjxb_model mjxb_model;
 
 int mjxb_abi_version(void);
+/* number of kernels this library has launched in the process so far (a CUDA-graph replay of captured launches is not counted) */
+long long mjxb_launch_count(void);
 size_t mjxb_blob_sizeof(void);
 size_t mjxb_env_config_sizeof(void);
 const char* mjxb_strerror(int code);

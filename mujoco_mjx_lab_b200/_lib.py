@@ -20,7 +20,7 @@ ERRORS = {0: "ok", -1: "invalid argument", -2: "bad model blob", -3: "CUDA error
           -5: "unsupported model"}
 
 # every symbol include/mjxb.h declares (tests check that the built library exports all of them)
-SYMBOLS = ("mjxb_abi_version", "mjxb_blob_sizeof", "mjxb_env_config_sizeof", "mjxb_strerror", "mjxb_last_cuda_error",
+SYMBOLS = ("mjxb_abi_version", "mjxb_launch_count", "mjxb_blob_sizeof", "mjxb_env_config_sizeof", "mjxb_strerror", "mjxb_last_cuda_error",
            "mjxb_model_create", "mjxb_model_create_ex", "mjxb_model_flags", "mjxb_model_reserve", "mjxb_ffma_peak", "mjxb_model_destroy", "mjxb_model_dims", "mjxb_model_scratch_bytes", "mjxb_launch_config", "mjxb_reset", "mjxb_step",
            "mjxb_step_autoreset", "mjxb_physics_step", "mjxb_forward", "mjxb_speed_test", "mjxb_reset_host", "mjxb_step_host",
            "mjxb_step_autoreset_host", "mjxb_state_get_host", "mjxb_state_set_host", "mjxb_policy_pack_weight", "mjxb_policy_act", "mjxb_gae", "mjxb_tanh_bwd_colsum")
@@ -60,6 +60,7 @@ def lib(variant: str = "fast") -> C.CDLL:
                         "(the CUDA extension is mandatory; there is no CPU fallback)")
     L = C.CDLL(path)
     L.mjxb_abi_version.restype = C.c_int
+    L.mjxb_launch_count.restype = C.c_longlong
     L.mjxb_blob_sizeof.restype = C.c_size_t
     L.mjxb_env_config_sizeof.restype = C.c_size_t
     L.mjxb_model_scratch_bytes.restype = C.c_size_t

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 #include <new>
 #include <vector>
@@ -15,6 +16,9 @@
 #include "mjxb_device.cuh"
 
 using namespace mjxb;
+
+// every kernel this library launches is counted here (bench.py reports the count of its timed region as `gpu_launches`)
+std::atomic<long long> g_mjxb_launches{0};
 
 namespace {
 
@@ -207,6 +211,7 @@ int launch(const mjxb_model* m, const StepArgs& args_in, bool dbg, cudaStream_t 
   const bool single = !dbg && ls && args.nsteps == 1 && (!(args.mode == MODE_ENV_STEP && args.autoreset) || args.reset_list != nullptr);
   if (single) mjxb_step_kernel<false, CAP_MAIN, MAXCC_MAIN, WARPS_MAIN, true, true><<<grid, warps * 32, smem_main, stream>>>(m->dev, m->dev_pp, args);
   else MJXB_LAUNCH(CAP_MAIN, MAXCC_MAIN, WARPS_MAIN, grid, warps * 32, smem_main);
+  g_mjxb_launches += 3;   // main tier + the two overflow tiers below (each leaves at once when its list is empty)
   cudaError_t e = cudaGetLastError();
   const bool sync_tiers = m->tune.sync_tiers;  // debugging aid: attribute a device fault to its tier
   if (sync_tiers && e == cudaSuccess) { e = cudaStreamSynchronize(stream); if (e != cudaSuccess) fprintf(stderr, "[mjxb] main tier failed: %s\n", cudaGetErrorString(e)); }
@@ -246,6 +251,7 @@ bool state_ok(const mjxb_state& s, bool need_aux) {
 extern "C" {
 
 int mjxb_abi_version(void) { return MJXB_ABI_VERSION; }
+long long mjxb_launch_count(void) { return g_mjxb_launches.load(); }
 size_t mjxb_blob_sizeof(void) { return sizeof(mjxb_model_blob); }
 size_t mjxb_env_config_sizeof(void) { return sizeof(mjxb_env_config); }
 const char* mjxb_last_cuda_error(void) { return g_cuda_err; }

@@ -12,11 +12,14 @@
 //   B (weights W^T, N rows x K):     byte(n,k) = (n%8)*16 + (n/8)*(K/8)*128 + (k/8)*128 + (k%8)*2 -> SBO = 16*K, LBO = 128
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <atomic>
 #include <mutex>
 #include <stdint.h>
 #include <stdio.h>
 
 #include "mjxb.h"
+
+extern std::atomic<long long> g_mjxb_launches;
 
 namespace mjxbp {
 
@@ -359,6 +362,7 @@ int mjxb_tanh_bwd_colsum(int32_t n, int32_t c, const float* dy, const float* y, 
   int grid = (n + 63) / 64;
   if (grid > 148 * 8) grid = 148 * 8;
   const int threads = c >= 256 ? 256 : ((c + 31) / 32) * 32;
+  g_mjxb_launches++;
   mjxbp::tanh_bwd_colsum_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(n, c, dy, y, dz, db_zeroed);
   return cudaGetLastError() == cudaSuccess ? MJXB_OK : MJXB_ECUDA;
 }
@@ -366,6 +370,7 @@ int mjxb_tanh_bwd_colsum(int32_t n, int32_t c, const float* dy, const float* y, 
 int mjxb_gae(int32_t rollout_length, int32_t n_env, const float* reward, const float* value, const float* terminated,
              const float* truncated, float gamma, float lam, float* advantage, float* ret, void* stream) {
   if (rollout_length <= 0 || n_env <= 0 || !reward || !value || !terminated || !truncated || !advantage || !ret) return MJXB_EINVAL;
+  g_mjxb_launches++;
   mjxbp::gae_kernel<<<(n_env + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rollout_length, n_env, reward, value, terminated, truncated,
                                                                            gamma, lam, advantage, ret);
   return cudaGetLastError() == cudaSuccess ? MJXB_OK : MJXB_ECUDA;
@@ -374,6 +379,7 @@ int mjxb_gae(int32_t rollout_length, int32_t n_env, const float* reward, const f
 int mjxb_policy_pack_weight(const float* w, int32_t k, int32_t n, int32_t k_pad, int32_t n_pad, void* out_bf16, void* stream) {
   if (!w || !out_bf16 || k <= 0 || n <= 0 || k_pad < k || n_pad < n || (k_pad % 16) || (n_pad % 16)) return MJXB_EINVAL;
   const int total = n_pad * k_pad;
+  g_mjxb_launches++;
   mjxbp::pack_weight_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, k, n, k_pad, n_pad, (__nv_bfloat16*)out_bf16);
   return cudaGetLastError() == cudaSuccess ? MJXB_OK : MJXB_ECUDA;
 }
@@ -406,6 +412,7 @@ int mjxb_policy_act(int32_t n_env, int32_t obs_dim, int32_t act_dim, const float
   }
   P.log_std = log_std; P.eps = eps; P.act = act; P.logp = logp; P.mean = mean; P.error = error_flag;
   const int grid = (n_env + mjxbp::kTile - 1) / mjxbp::kTile;
+  g_mjxb_launches++;
   mjxbp::policy_act_kernel<<<grid, mjxbp::kThreads, mjxbp::kSmemBytes, (cudaStream_t)stream>>>(P);
   return cudaGetLastError() == cudaSuccess ? MJXB_OK : MJXB_ECUDA;
 }

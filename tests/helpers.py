@@ -87,3 +87,44 @@ def ppo_keys(seed, n):
     rng = jax_random.PRNGKey(seed)
     _, k = jax_random.split(rng, 2)
     return jax_random.split(k, n)
+
+
+# ---------------------------------------------------------------- host build of the reverse-mode step (tests/adjoint_host.cpp)
+_ADJ_LIB = None
+
+
+def adjoint_host():
+    """ctypes handle of tests/_build/libadjoint_host.so: csrc/mjxb_adjoint.cuh compiled for the CPU in double (test harness only)."""
+    global _ADJ_LIB
+    if _ADJ_LIB is not None:
+        return _ADJ_LIB
+    import ctypes as C
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = os.path.join(here, "_build", "libadjoint_host.so")
+    srcs = [os.path.join(here, "adjoint_host.cpp")] + [os.path.join(ROOT, "mujoco_mjx_lab_b200", "csrc", f) for f in ("mjxb_adjoint.cuh", "mjxb_model_dev.h")]
+    if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-I" + os.path.join(ROOT, "include"), "-o", out, srcs[0]],
+                       check=True, capture_output=True)
+    _ADJ_LIB = C.CDLL(out)
+    return _ADJ_LIB
+
+
+def tangent_perturb(model, q, d, eps):
+    """qpos moved by eps along tangent coordinate d (dof index): hinge / free translation add, free rotation q (x) exp(eps e_k / 2)."""
+    q = np.array(q, dtype=np.float64)
+    if d < 3:
+        q[d] += eps
+    elif d < 6:
+        k = d - 3
+        r = np.zeros(4); r[0] = np.cos(eps / 2); r[1 + k] = np.sin(eps / 2)
+        w, x, y, z = q[3:7] / np.linalg.norm(q[3:7])
+        a = np.array([w, x, y, z])
+        q[3:7] = np.array([a[0] * r[0] - a[1] * r[1] - a[2] * r[2] - a[3] * r[3],
+                           a[0] * r[1] + a[1] * r[0] + a[2] * r[3] - a[3] * r[2],
+                           a[0] * r[2] - a[1] * r[3] + a[2] * r[0] + a[3] * r[1],
+                           a[0] * r[3] + a[1] * r[2] - a[2] * r[1] + a[3] * r[0]])
+    else:
+        q[d + 1] += eps
+    return q
