@@ -205,6 +205,23 @@ int mjxb_tanh_bwd_colsum(int32_t n, int32_t c, const float* dy, const float* y, 
 int mjxb_gae(int32_t rollout_length, int32_t n_env, const float* reward, const float* value, const float* terminated,
              const float* truncated, float gamma, float lam, float* advantage, float* ret, void* stream);
 
+/* ---- analytic policy gradients (reference train_apg.py:161-209: value_and_grad through lax.scan(jax.checkpoint(v_step))).
+ * mjxb_step_fwd_tape: v_step (src/envs.py:333-492, no auto-reset) that also records the tape of the reverse pass: the solver's qacc
+ *   tape_qacc[n, nv] (may alias out.qacc_warmstart, which holds the same numbers). Everything else the reverse pass needs is recomputed
+ *   from the step's inputs, which the caller keeps (as jax.checkpoint does).
+ * mjxb_step_vjp: vector-Jacobian product of that step. Given the step's inputs (`in`, `action`), the tape, and the cotangents of its
+ *   outputs -- g_qpos_out[n, nq], g_qvel_out[n, nv], g_aux_out[n, 9] (entries 1,2,3 = target and 7 = last_pot are used), g_reward[n]; any
+ *   may be NULL = zero -- it writes the cotangents of its inputs: g_qpos_in[n, nq] (quaternion components included), g_qvel_in[n, nv],
+ *   g_aux_in[n, 9], g_action[n, nu]. The constraint solve is differentiated by the implicit function theorem at the converged solution
+ *   (active set held fixed); discrete outputs (done flags, stance, target advance) have zero gradient; qacc_warmstart has zero gradient.
+ *   in.aux == NULL selects the physics step alone (mjx.step: `action` is ctrl, no env layer, g_aux_* / g_reward ignored).
+ *   Envs whose candidate rows exceed the 64-row tile are re-run by a 320-row instantiation inside the same call. */
+int mjxb_step_fwd_tape(const mjxb_model* m, int32_t n_env, mjxb_state in, const float* action, mjxb_state out, float* obs, float* reward,
+                       float* terminated, float* truncated, float* tape_qacc, int32_t* status, void* stream);
+int mjxb_step_vjp(const mjxb_model* m, int32_t n_env, mjxb_state in, const float* action, const float* tape_qacc,
+                  const float* g_qpos_out, const float* g_qvel_out, const float* g_aux_out, const float* g_reward, float* g_qpos_in,
+                  float* g_qvel_in, float* g_aux_in, float* g_action, int32_t* status, void* stream);
+
 /* Measurement aid (bench.py's roofline_fp32 denominator): the FP32 FMA-pipe throughput of `device`, measured with a kernel of
  * independent FFMA chains and no memory traffic (best of several repetitions; synchronises the device). */
 int mjxb_ffma_peak(int32_t device, float* tflops_out, float* ms_out);

@@ -23,7 +23,8 @@ ERRORS = {0: "ok", -1: "invalid argument", -2: "bad model blob", -3: "CUDA error
 SYMBOLS = ("mjxb_abi_version", "mjxb_launch_count", "mjxb_blob_sizeof", "mjxb_env_config_sizeof", "mjxb_strerror", "mjxb_last_cuda_error",
            "mjxb_model_create", "mjxb_model_create_ex", "mjxb_model_flags", "mjxb_model_reserve", "mjxb_ffma_peak", "mjxb_model_destroy", "mjxb_model_dims", "mjxb_model_scratch_bytes", "mjxb_launch_config", "mjxb_reset", "mjxb_step",
            "mjxb_step_autoreset", "mjxb_physics_step", "mjxb_forward", "mjxb_speed_test", "mjxb_reset_host", "mjxb_step_host",
-           "mjxb_step_autoreset_host", "mjxb_state_get_host", "mjxb_state_set_host", "mjxb_policy_pack_weight", "mjxb_policy_act", "mjxb_gae", "mjxb_tanh_bwd_colsum")
+           "mjxb_step_autoreset_host", "mjxb_state_get_host", "mjxb_state_set_host", "mjxb_policy_pack_weight", "mjxb_policy_act", "mjxb_gae", "mjxb_tanh_bwd_colsum",
+           "mjxb_step_fwd_tape", "mjxb_step_vjp")
 
 
 class MjxbError(RuntimeError):
@@ -81,6 +82,8 @@ def lib(variant: str = "fast") -> C.CDLL:
     L.mjxb_reset.argtypes = [vp, i32, vp, StateC, vp, vp, vp]
     L.mjxb_step.argtypes = [vp, i32, StateC, vp, StateC, vp, vp, vp, vp, vp, vp]
     L.mjxb_step_autoreset.argtypes = [vp, i32, StateC, vp, vp, StateC, vp, vp, vp, vp, vp, vp, vp]
+    L.mjxb_step_fwd_tape.argtypes = [vp, i32, StateC, vp, StateC, vp, vp, vp, vp, vp, vp, vp]
+    L.mjxb_step_vjp.argtypes = [vp, i32, StateC, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.mjxb_physics_step.argtypes = [vp, i32, StateC, vp, i32, C.POINTER(DebugC), vp, vp]
     L.mjxb_forward.argtypes = [vp, i32, StateC, vp, C.POINTER(DebugC), vp, vp]
     L.mjxb_speed_test.argtypes = [vp, i32, vp, vp, i32, vp]

@@ -14,6 +14,7 @@
 #endif
 #include "mjxb.h"
 #include "mjxb_device.cuh"
+#include "mjxb_internal.h"
 
 using namespace mjxb;
 
@@ -247,6 +248,16 @@ bool state_ok(const mjxb_state& s, bool need_aux) {
 }
 
 }  // namespace
+
+namespace mjxb {
+int model_view(const mjxb_model* m, ModelView* out) {
+  if (!m || !out) return MJXB_EINVAL;
+  out->host = &m->host; out->dev = m->dev; out->dev_pp = m->dev_pp; out->device = m->device; out->num_sms = m->num_sms;
+  return MJXB_OK;
+}
+int model_scratch(const mjxb_model* m, cudaStream_t stream, int n_env, int** buf, int* cap) { return scratch_for(m, stream, n_env, buf, cap); }
+int report_cuda_error(cudaError_t e, const char* what) { return cuda_fail(e, what); }
+}  // namespace mjxb
 
 extern "C" {
 

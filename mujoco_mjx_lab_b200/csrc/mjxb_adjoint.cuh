@@ -783,7 +783,8 @@ MJA_HDN void vjp_forward(const DevModel& C, const PairParam* pp, WS& W, Lanes X,
   }
   X.sync();
   MJA_FOR(i, C.nu) {
-    const bool flip = io.aux != nullptr && W.aux[0] > T(0.5);
+    if (io.aux == nullptr) { W.u[i] = io.action[i]; W.uclip[i] = T(1); continue; }   // physics-only: `action` is ctrl (mjx.step)
+    const bool flip = W.aux[0] > T(0.5);
     const T val = flip ? io.action[cfg.act_perm[i]] * T(cfg.act_sign[i]) : io.action[i];
     W.u[i] = clampT(val, T(-1), T(1));
     W.uclip[i] = (val > T(-1) && val < T(1)) ? T(1) : T(0);
