@@ -35,7 +35,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/ -> libmjxb.so with nvcc for sm_100a (cross-compiles without a GPU)."""
     csrc = os.path.join(_HERE, "csrc")
     inc = os.path.join(_HERE, "..", "include")
-    srcs = [os.path.join(csrc, f) for f in sorted(os.listdir(csrc)) if f.endswith((".cu", ".cuh", ".h", ".cc", "Makefile"))]
+    srcs = [os.path.join(csrc, f) for f in sorted(os.listdir(csrc)) if f.endswith((".cu", ".cuh", ".h"))]
     srcs += [os.path.join(inc, f) for f in ("mjxb.h", "mjxb_model.h")]
     for target in (LIB_PATH, EXACT_LIB_PATH):
         stale = force or not os.path.exists(target) or any(os.path.getmtime(s) > os.path.getmtime(target) for s in srcs)

@@ -73,11 +73,13 @@ def diff_step(sysm, state, action):
     return (Data(qpos2, qvel2, warm2, tm2), aux2), obs, reward, term, trunc
 
 
-def _policy_params(in_dim, hidden, depth, out_dim, gen, device):
+def _policy_params(in_dim, hidden, depth, out_dim, gen, device, output_scale: float = 1.0):
     dims = [in_dim] + [hidden] * depth + [out_dim]
     params = []
-    for a, b in zip(dims[:-1], dims[1:]):
+    for i, (a, b) in enumerate(zip(dims[:-1], dims[1:])):
         w = torch.randn(a, b, generator=gen, device=device) * math.sqrt(2.0 / (a + b))      # reference src/networks.py:44-47
+        if i == len(dims) - 2:
+            w = w * output_scale
         params += [w.requires_grad_(), torch.zeros(b, device=device, requires_grad=True)]
     return params
 
@@ -93,7 +95,7 @@ def _policy_apply(params, x):
 
 
 class APGTrainer:
-    def __init__(self, cfg: APGConfig, v_reset, v_step, batch_size_local: int, env_cfg=None, seed: int = 0):
+    def __init__(self, cfg: APGConfig, v_reset, v_step, batch_size_local: int, env_cfg=None, seed: int = 0, output_scale: float = 1.0):
         self.cfg, self.v_reset, self.v_step = cfg, v_reset, v_step
         self.sys = v_step.sys
         self.dev = self.sys.device
@@ -103,7 +105,7 @@ class APGTrainer:
             parallel.init("nccl")
         self.obs_dim = self.sys.nq + self.sys.nv                                  # reference train_apg.py:119
         gen = torch.Generator(device=self.dev).manual_seed(seed)
-        self.params = _policy_params(self.obs_dim, cfg.hidden_size, cfg.hidden_depth, self.sys.nu, gen, self.dev)
+        self.params = _policy_params(self.obs_dim, cfg.hidden_size, cfg.hidden_depth, self.sys.nu, gen, self.dev, output_scale)
         self.opt = torch.optim.Adam(self.params, lr=cfg.lr, eps=1e-8)
         self.obs_mean = torch.zeros(self.obs_dim, device=self.dev)
         self.obs_var = torch.ones(self.obs_dim, device=self.dev)
@@ -122,9 +124,12 @@ class APGTrainer:
             d, aux = state
             obs = torch.cat([d.qpos, d.qvel], dim=1)
             x = torch.clamp((obs - self.obs_mean) / (torch.sqrt(self.obs_var) + 1e-8), -10.0, 10.0) if use_norm else obs
-            act = _policy_apply(self.params, x)
+            act = _policy_apply(self.params, torch.nan_to_num(x, nan=0.0, posinf=1e6, neginf=-1e6))
             state, _, r, te, tr = diff_step(self.sys, state, act)
             done = torch.maximum(te, tr)
+            # (an env that already finished contributes nothing; it keeps stepping without reset as in the reference, and a body that
+            #  has numerically diverged AFTER its episode ended must not turn 0 * nan into nan)
+            r = torch.where(disc > 0, r, torch.zeros_like(r))
             acc = acc + disc * r
             disc = disc * self.cfg.gamma * (1.0 - done)
             obs_traj.append(obs.detach())
@@ -162,7 +167,7 @@ class APGTrainer:
             self.obs_mean, self.obs_var, self.obs_count = mean.float(), torch.clamp_min(m2 / tot, 1e-4).float(), tot
         self.step_no += 1
         torch.cuda.synchronize()
-        out = {"loss": float(loss), "mean_reward": float(mean_reward), "grad_norm": float(grad_norm),
+        out = {"loss": float(loss.detach()), "mean_reward": float(mean_reward), "grad_norm": float(grad_norm),
                "forward_ms": ev[0].elapsed_time(ev[1]), "backward_ms": ev[1].elapsed_time(ev[2]), "update_ms": ev[0].elapsed_time(ev[2])}
         if not math.isfinite(out["loss"]):
             raise RuntimeError("non-finite APG loss (reference train_apg.py:278-287 stops here as well)")
@@ -180,11 +185,15 @@ def make_apg_env(model=None, env_cfg=None):
     return cfg, out
 
 
-def time_apg(batch_size_local: int, horizon: int, iters: int = 3, warmup: int = 2, hidden_size: int = 32) -> Dict[str, float]:
-    """Times APG updates (forward rollout + reverse sweep + optimiser), device-synchronised, max over ranks."""
+def time_apg(batch_size_local: int, horizon: int, iters: int = 3, warmup: int = 2, hidden_size: int = 32,
+             output_scale: float = 0.01) -> Dict[str, float]:
+    """Times APG updates (forward rollout + reverse sweep + optimiser), device-synchronised, max over ranks.
+    `output_scale` shrinks the random-init action head: with the reference's Xavier-scale head, velocity feedback through 40-120 N m
+    gears makes the CG-4/4 physics of train_apg.py:101-105 diverge to non-finite states within ~30 of the 128 steps (the CPU restatement
+    of mjx.step does the same, tools/apg_stability_probe.py), and the reference's trainer stops on a non-finite loss (train_apg.py:278)."""
     cfg, env = make_apg_env()
     cfg.horizon, cfg.hidden_size = horizon, hidden_size
-    tr = APGTrainer(cfg, env[8], env[9], batch_size_local)
+    tr = APGTrainer(cfg, env[8], env[9], batch_size_local, output_scale=output_scale)
     for _ in range(warmup):
         tr.update()
     parallel.barrier()
@@ -201,5 +210,6 @@ def time_apg(batch_size_local: int, horizon: int, iters: int = 3, warmup: int = 
     res = {k: parallel.max_over_ranks(v / iters, tr.dev) for k, v in acc.items()}
     res.update(wall_update_ms=wall, envs_per_gpu=batch_size_local, horizon=horizon, world=tr.world, solver="CG 4/4 (train_apg.py:101-105)",
                env_steps_per_sec=batch_size_local * tr.world * horizon / (wall * 1e-3), loss=last.get("loss"), grad_norm=last.get("grad_norm"),
+               policy_output_scale=output_scale,
                reverse_mode="mjxb_step_vjp (implicit-function adjoint of the solve, hand-written kernels)")
     return res

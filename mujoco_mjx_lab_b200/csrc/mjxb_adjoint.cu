@@ -51,7 +51,8 @@ __global__ void __launch_bounds__(256, 1) step_vjp_kernel(const DevModel* __rest
     const int st = adj::step_vjp_env<float>(C, pair_param, W, X, io);
     if (lane == 0) {
       if (st == adj::VJP_OVERFLOW && A.out_list != nullptr) { const int slot = atomicAdd(A.out_count, 1); A.out_list[slot] = (int)env; }
-      if (A.status) A.status[env] = (consuming ? MJXB_STATUS_ROW_SPILL : 0) | (st == adj::VJP_OVERFLOW && A.out_list == nullptr ? MJXB_STATUS_ROW_SPILL | MJXB_STATUS_NAN : 0);
+      if (A.status) A.status[env] = (consuming ? MJXB_STATUS_ROW_SPILL : 0) | (st == adj::VJP_NONFINITE ? MJXB_STATUS_NAN : 0) |
+                                    (st == adj::VJP_OVERFLOW && A.out_list == nullptr ? MJXB_STATUS_ROW_SPILL | MJXB_STATUS_NAN : 0);
     }
     __syncwarp();
   }

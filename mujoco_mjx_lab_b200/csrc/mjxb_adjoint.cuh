@@ -49,7 +49,7 @@ struct Lanes {
 #define MJA_FOR(i, count) for (int i = X.lane; i < (count); i += X.n)
 
 constexpr int NB = MJXB_MAXBODY, NG = MJXB_MAXGEOM, NJ = MJXB_MAXJNT;
-enum { VJP_OK = 0, VJP_OVERFLOW = 1 };
+enum { VJP_OK = 0, VJP_OVERFLOW = 1, VJP_NONFINITE = 2 };
 
 // ------------------------------------------------------------------------------------------- small math (templated: float on the GPU)
 template <class T> MJA_HD T dot3(const T* a, const T* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
@@ -1300,6 +1300,24 @@ MJA_HDN int step_vjp_env(const DevModel& C, const PairParam* pp, WS& W, Lanes X,
     }
   }
   X.sync();
+  // A state that has already diverged (non-finite inputs, or a pull-back that overflowed) must not poison the rest of the batch through
+  // the optimiser: its cotangents are zeroed and the caller is told (VJP_NONFINITE -> MJXB_STATUS_NAN).
+  if (X.lane == 0) {
+    bool ok = true;
+    for (int i = 0; i < C.nq; i++) ok = ok && (absT(io.g_qpos_in[i]) < T(1e30));
+    for (int i = 0; i < NV; i++) ok = ok && (absT(io.g_qvel_in[i]) < T(1e30));
+    for (int i = 0; i < C.nu; i++) ok = ok && (absT(io.g_action[i]) < T(1e30));
+    if (io.g_aux_in) for (int i = 0; i < MJXB_AUX_DIM; i++) ok = ok && (absT(io.g_aux_in[i]) < T(1e30));
+    W.red[0] = ok ? T(1) : T(0);
+    if (!ok) {
+      for (int i = 0; i < C.nq; i++) io.g_qpos_in[i] = T(0);
+      for (int i = 0; i < NV; i++) io.g_qvel_in[i] = T(0);
+      for (int i = 0; i < C.nu; i++) io.g_action[i] = T(0);
+      if (io.g_aux_in) for (int i = 0; i < MJXB_AUX_DIM; i++) io.g_aux_in[i] = T(0);
+    }
+  }
+  X.sync();
+  if (W.red[0] == T(0)) return VJP_NONFINITE;
   return W.overflow ? VJP_OVERFLOW : VJP_OK;
 }
 
