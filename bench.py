@@ -319,6 +319,31 @@ def main():
         val, dt, threads = cpu_reference_run(ncpu, 4, 1)
         line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": f"{ncpu} envs x 4 steps of the same workload, CPU oracle (float32 restatement of mjx.step + src/envs.py), {dt:.1f} s"}
+    # BASELINE configs[0]: the reference's own CPU-runnable case -- mjx_humanoid_speed_test.py semantics at 64 envs -- on this box's host
+    # cores with the CPU restatement (MJX-on-CPU itself is UNAVAILABLE here, see north_star_cpu_baselines), beside the GPU's N=64 sweep row
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import helpers
+            from oracle import oracle as O
+            O.build()
+            orc1 = helpers.make_oracle(model)
+            try:
+                orc1.nthreads = len(os.sched_getaffinity(0))
+            except AttributeError:
+                orc1.nthreads = os.cpu_count() or 1
+            vel64 = np.linspace(0, 1, 64)
+            orc1.speed_test(vel64, iters=2)
+            t0 = time.perf_counter()
+            it1 = 20
+            orc1.speed_test(vel64, iters=it1)
+            dt1 = time.perf_counter() - t0
+            gpu64 = next((r for r in sweep if r["n_env"] == 64), None)
+            line["config1_cpu_sanity"] = {"workload": "mjx_humanoid_speed_test.py:48-57 step, humanoid_mjx.xml, 64 envs", "cpu_env_steps_per_sec": 64 * it1 / dt1,
+                                          "cpu_kind": "port (CPU restatement of mjx.step, float32)", "cores": orc1.nthreads, "iters": it1,
+                                          "gpu_env_steps_per_sec_same_workload": gpu64["speedtest_steps_per_s"] if gpu64 else None}
+        except Exception as e:
+            line["config1_cpu_sanity"] = {"error": f"{type(e).__name__}: {e}"}
     # the two CPU baselines north_star names (MuJoCo C, MJX on JAX-CPU): self-reporting scripts, UNAVAILABLE in this image
     if world == 1:
         nsb = {}
