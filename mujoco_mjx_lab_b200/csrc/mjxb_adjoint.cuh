@@ -130,6 +130,8 @@ struct AdjS {
   T Zv[NV][6], Za[NV][6], Zl[NV][6];  // twist prefixes sum_{e<=d} S_e z_e for z = qvel, qacc, lambda (contact-row cotangents)
   T M[NV][NVP];
   T L[NV][NV];
+  T col[2][32];                   // GPU Cholesky: column broadcast buffer (double buffered)
+  T dinvA[32];                    // 1 / diag of the factor of M + h D (kept for the second solve with that factor)
   T gpos[NG][3], gaxis[NG][3];
   unsigned char pflag[MJXB_MAXPAIR];
   // contacts
@@ -702,6 +704,54 @@ MJA_HD void chol_solve(WS& W, Lanes X, T* x /* in: rhs, out: solution (workspace
   X.sync();
 }
 
+#if defined(__CUDA_ARCH__)
+// GPU: row `lane` of the SPD matrix lives in registers (a[0..NV), lower part used); column k is broadcast through W.col. On return
+// a[k] (k < lane) = L[lane][k], dinv = 1 / L[lane][lane], and the rows are stored to W.L for the backward substitutions.
+template <class WS>
+__device__ __forceinline__ void gpu_chol_rows(WS& W, int lane, float (&a)[NVP], float& dinv) {
+  dinv = 1.0f;
+#pragma unroll
+  for (int k = 0; k < NV; k++) {
+    const float akk = __shfl_sync(0xffffffffu, a[k], k);
+    const float inv = rsqrtf(akk);
+    const float lik = a[k] * inv;          // valid for lane > k; lane k gets sqrt(akk)
+    if (lane == k) dinv = inv;
+    a[k] = lik;
+    if (k + 1 < NV) {
+      float* col = W.col[k & 1];
+      col[lane] = lik;
+      __syncwarp();
+#pragma unroll
+      for (int j = k + 1; j < NV; j++) a[j] -= lik * col[j];
+    }
+  }
+  __syncwarp();
+  if (lane < NV) {
+#pragma unroll
+    for (int k = 0; k < NV; k++) W.L[lane][k] = (k < lane) ? a[k] : (k == lane ? 1.0f / dinv : 0.0f);
+  }
+  __syncwarp();
+}
+// solve (L L^T) x = b from the rows in W.L and the lane's 1 / L_ii
+template <class WS>
+__device__ __forceinline__ float gpu_chol_solve(const WS& W, int lane, float dinv, float b) {
+  const int row = lane < NV ? lane : 0;
+  float y = lane < NV ? b : 0.0f;
+#pragma unroll
+  for (int k = 0; k < NV; k++) {
+    const float yk = __shfl_sync(0xffffffffu, y * dinv, k);
+    if (lane > k && lane < NV) y -= W.L[row][k] * yk;
+  }
+  float x = y * dinv;
+#pragma unroll
+  for (int k = NV - 1; k >= 0; k--) {
+    const float xk = __shfl_sync(0xffffffffu, x * dinv, k);
+    if (lane < k) x -= W.L[k][row] * xk;
+  }
+  return x * dinv;
+}
+#endif
+
 // ------------------------------------------------------------------------------------------- gradient of sign * lam^T ID(q, vv, aa)
 // ID = inverse dynamics M(q) aa + c(q, vv) (gravity optional). Accumulates into W.Sbar (cotangents of the joint motion axes S_e),
 // W.Hacc (inertia-variation pseudo-forces summed over the bodies each dof moves) and W.gv (gradient with respect to vv).
@@ -818,6 +868,24 @@ MJA_HDN void vjp_forward(const DevModel& C, const PairParam* pp, WS& W, Lanes X,
     W.pflag[p] = fl;
   }
   X.sync();
+#if defined(__CUDA_ARCH__)
+  {  // ordered compaction by ballots: a strip of 32 pairs, endpoint 0 and endpoint 1 interleaved in pair order
+    int ncc = 0, ovf = 0;
+    const unsigned lt = (1u << X.lane) - 1u;
+    for (int base = 0; base < C.npair; base += 32) {
+      const int p = base + X.lane;
+      const unsigned fl = p < C.npair ? W.pflag[p] : 0u;
+      const unsigned m0 = __ballot_sync(0xffffffffu, fl & 1u), m1 = __ballot_sync(0xffffffffu, fl & 2u);
+      const int before = ncc + __popc(m0 & lt) + __popc(m1 & lt);
+      const int cd = p < C.npair ? (int)((C.pair_w0[p] >> 24) & 0x7f) << 20 : 0;
+      if (fl & 1u) { if (before < WS::MAXCC) W.cc_pair[before] = p | cd; else ovf = 1; }
+      if (fl & 2u) { const int i1 = before + ((fl & 1u) ? 1 : 0); if (i1 < WS::MAXCC) W.cc_pair[i1] = p | (1 << 16) | cd; else ovf = 1; }
+      ncc += __popc(m0) + __popc(m1);
+    }
+    ovf = __any_sync(0xffffffffu, ovf) ? 1 : 0;
+    if (X.lane == 0) { W.ncc = ncc > WS::MAXCC ? WS::MAXCC : ncc; W.overflow = ovf; }
+  }
+#else
   if (X.lane == 0) {
     int ncc = 0, ovf = 0;
     for (int p = 0; p < C.npair; p++)
@@ -830,6 +898,7 @@ MJA_HDN void vjp_forward(const DevModel& C, const PairParam* pp, WS& W, Lanes X,
     W.ncc = ncc > WS::MAXCC ? WS::MAXCC : ncc;
     W.overflow = ovf;
   }
+#endif
   X.sync();
   MJA_FOR(c, W.ncc) {
     const int pr = W.cc_pair[c], p = pr & 0xffff, e = (pr >> 16) & 0xf;
@@ -925,10 +994,25 @@ MJA_HDN void vjp_forward(const DevModel& C, const PairParam* pp, WS& W, Lanes X,
     W.x[i] = damp ? s : W.a[i];
   }
   if (damp) {
+#if defined(__CUDA_ARCH__)
+    {
+      X.sync();
+      const int lane = X.lane, row = lane < NV ? lane : 0;
+      float a[NVP], dinv;
+#pragma unroll
+      for (int j = 0; j < NVP; j++) a[j] = (lane < NV && j < NV) ? (float)W.M[row][j] + (j == lane ? (float)h * C.dof_damping[row] : 0.0f) : (j == lane ? 1.0f : 0.0f);
+      gpu_chol_rows(W, lane, a, dinv);
+      W.dinvA[lane] = dinv;
+      const float xs = gpu_chol_solve(W, lane, dinv, (float)W.x[row]);
+      __syncwarp();
+      if (lane < NV) W.x[lane] = xs;
+    }
+#else
     MJA_FOR(i, NV) for (int j = 0; j < NV; j++) W.L[i][j] = W.M[i][j] + (i == j ? h * T(C.dof_damping[i]) : T(0));
     X.sync();
     chol_factor<T>(W, X);
     chol_solve<T>(W, X, W.x);
+#endif
   }
   X.sync();
   MJA_FOR(i, 32) W.vnew[i] = i < NV ? W.v[i] + h * W.x[i] : T(0);
@@ -1083,7 +1167,16 @@ MJA_HDN int step_vjp_env(const DevModel& C, const PairParam* pp, WS& W, Lanes X,
   MJA_FOR(i, 32) W.y[i] = i < NV ? W.xbar[i] : T(0);
   X.sync();
   if (damp) {
+#if defined(__CUDA_ARCH__)
+    {
+      const float ys = gpu_chol_solve(W, X.lane, (float)W.dinvA[X.lane], (float)W.y[X.lane < NV ? X.lane : 0]);
+      __syncwarp();
+      if (X.lane < NV) W.y[X.lane] = ys;
+      __syncwarp();
+    }
+#else
     chol_solve<T>(W, X, W.y);
+#endif
     MJA_FOR(i, NV) {
       T s = T(0);
       for (int j = 0; j < NV; j++) s += W.M[i][j] * W.y[j];
@@ -1094,6 +1187,26 @@ MJA_HDN int step_vjp_env(const DevModel& C, const PairParam* pp, WS& W, Lanes X,
   }
   X.sync();
   // ---- (4) implicit-function adjoint of the solve: H lam = abar, H = M + sum_active D_r J_r J_r^T
+#if defined(__CUDA_ARCH__)
+  {
+    X.sync();
+    const int lane = X.lane, row = lane < NV ? lane : 0;
+    float a[NVP], dinv;
+#pragma unroll
+    for (int j = 0; j < NVP; j++) a[j] = (lane < NV && j < NV) ? (float)W.M[row][j] : (j == lane ? 1.0f : 0.0f);
+    for (int r = 0; r < W.nrow; r++) {
+      if (!W.ract[r]) continue;                         // warp-uniform
+      const float w = lane < NV ? (float)(W.rD[r] * W.J[r][row]) : 0.0f;
+#pragma unroll
+      for (int j = 0; j < NV; j++) a[j] += w * (float)W.J[r][j];
+    }
+    gpu_chol_rows(W, lane, a, dinv);
+    const float ls = gpu_chol_solve(W, lane, dinv, (float)W.abar[row]);
+    __syncwarp();
+    W.lam[lane] = lane < NV ? ls : 0.0f;
+    __syncwarp();
+  }
+#else
   MJA_FOR(i, NV) {
     for (int j = 0; j < NV; j++) {
       T s = W.M[i][j];
@@ -1106,6 +1219,7 @@ MJA_HDN int step_vjp_env(const DevModel& C, const PairParam* pp, WS& W, Lanes X,
   X.sync();
   chol_factor<T>(W, X);
   chol_solve<T>(W, X, W.lam);
+#endif
   twist_prefix<T>(C, W, X, W.lam, W.Zl);
   // rows: w = J lam ; cotangents of aref / D / pos ; direct terms in v ; relative-twist form of the contact-row cotangent phibar
   MJA_FOR(r, W.nrow) {
