@@ -62,7 +62,7 @@ struct Arena {  // device-resident env batch for the *_host entry points
 struct Tuning {
   int lockstep = 1;        // 1: CTA barriers at the round top and at the solver entry / exit; 3: also at every factor/solve round; 0: none
   int lockstep_group = 0;  // warps per barrier group (0 = the whole CTA)
-  bool inline_reset = false, sync_tiers = false;
+  bool inline_reset = false, sync_tiers = false, spec_reset = true;
   bool host_direct = true, direct_obs = true, direct_scalars = true;
   int host_chunks = 0;
 };
@@ -198,6 +198,17 @@ int launch(const mjxb_model* m, const StepArgs& args_in, bool dbg, cudaStream_t 
   if (per_sm < warps) warps = per_sm < 1 ? 1 : per_sm;
   int grid = (args.n_env + warps - 1) / warps;
   if (grid > m->num_sms) grid = m->num_sms;
+  const bool ls_ = m->host.ls_exact != 0 && m->host.solver == 2;
+  const bool single_ = !dbg && ls_ && args.nsteps == 1 && (!(args.mode == MODE_ENV_STEP && args.autoreset) || args.reset_list != nullptr);
+  // speculative auto-reset while every SM has idle warps (two warps per env fit): the re-initialisation of an env that finishes its
+  // episode runs beside its step instead of as a second pass after it (bit-identical results; ~2x lower step latency at <= 1184 envs)
+  args.spec_reset = 0;
+  if (m->tune.spec_reset && single_ && args.mode == MODE_ENV_STEP && args.autoreset && 2 * per_sm <= m->warps) {
+    args.spec_reset = 1;
+    warps = 2 * (per_sm < 1 ? 1 : per_sm);
+    grid = (args.n_env + per_sm - 1) / per_sm;
+    if (grid > m->num_sms) grid = m->num_sms;
+  }
   const size_t smem_main = m->smem - (size_t)(m->warps - warps) * sizeof(WarpS<CAP_MAIN, MAXCC_MAIN>);
   args.reset_stride = ((args.n_env + grid * warps - 1) / (grid * warps)) * warps;
   const bool ls = m->host.ls_exact != 0 && m->host.solver == 2;  // fast instantiation: Newton + exact line search; else the general one
@@ -320,6 +331,7 @@ int mjxb_model_create_ex(const void* blob, size_t blob_bytes, const mjxb_env_con
   m->tune.lockstep = env_int("MJXB_LOCKSTEP", 1);
   m->tune.lockstep_group = env_int("MJXB_LOCKSTEP_GROUP", 0);
   m->tune.sync_tiers = getenv("MJXB_SYNC_TIERS") != nullptr;
+  m->tune.spec_reset = env_int("MJXB_SPEC_RESET", 1) != 0 && !m->tune.inline_reset && !(flags & MJXB_FLAG_NO_SPEC_RESET);
   m->tune.host_chunks = env_int("MJXB_HOST_CHUNKS", 0);
   m->tune.host_direct = env_int("MJXB_HOST_DIRECT", 1) != 0;
   m->tune.direct_obs = env_int("MJXB_DIRECT_OBS", 1) != 0;
@@ -409,6 +421,7 @@ int mjxb_model_flags(const mjxb_model* m) {
   if (!m->host.ls_exact) f |= MJXB_FLAG_LS_ITERATIVE;
   if (!m->host.tree_chol_ok) f |= MJXB_FLAG_DENSE_CHOL;
   if (m->tune.inline_reset) f |= MJXB_FLAG_INLINE_RESET;
+  if (!m->tune.spec_reset) f |= MJXB_FLAG_NO_SPEC_RESET;
 #if MJXB_EXACT
   f |= MJXB_FLAG_BUILD_EXACT;
 #endif

@@ -10,7 +10,7 @@
 
 namespace mjxb {
 
-constexpr int VJP_CAP = 64, VJP_MAXCC = 24;   // main tile: rows / contacts of one env; envs that need more go to the CAP_BIG tile
+constexpr int VJP_CAP = 48, VJP_MAXCC = 20;   // main tile: rows / contacts of one env; envs that need more go to the CAP_BIG tile
 
 struct VjpArgs {
   int n_env;

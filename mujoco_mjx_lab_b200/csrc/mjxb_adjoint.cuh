@@ -127,7 +127,10 @@ struct AdjS {
   T cinert[NB][10];
   T S[NV][6];                     // cdof
   T V[NV][6], Sd[NV][6], A[NV][6];  // inclusive velocity prefix, cdof_dot, inclusive acceleration prefix (of the current idgrad call)
-  T Zv[NV][6], Za[NV][6], Zl[NV][6];  // twist prefixes sum_{e<=d} S_e z_e for z = qvel, qacc, lambda (contact-row cotangents)
+  union {   // lifetimes do not overlap: the twist prefixes feed the contact-row cotangents, the per-body scratch belongs to idgrad (later)
+    struct { T Zv[NV][6], Za[NV][6], Zl[NV][6]; };  // twist prefixes sum_{e<=d} S_e z_e for z = qvel, qacc, lambda
+    struct { T tb0[NB][6], tb1[NB][6], tb2[NB][6], tb3[NB][6]; };   // per-body scratch
+  };
   T M[NV][NVP];
   T L[NV][NV];
   T col[2][32];                   // GPU Cholesky: column broadcast buffer (double buffered)
@@ -149,9 +152,10 @@ struct AdjS {
   T xbar[32], abar[32], lam[32], y[32], wv[32];
   T gqt[32], gv[32], ubar[32], gqdirect[32];
   T Sbar[NV][6], Hacc[NV][6], Wb[NB][6];
-  T tb0[NB][6], tb1[NB][6], tb2[NB][6], tb3[NB][6];   // per-body scratch
-  T td0[NV][6], td1[NV][6], td2[NV][6];               // per-dof scratch
-  T crb[NB][10];
+  union {   // composite inertias are consumed by the mass matrix before any per-dof scratch is written
+    struct { T td0[NV][6], td1[NV][6], td2[NV][6]; };  // per-dof scratch
+    T crb[NB][10];
+  };
   T gauxin[MJXB_AUX_DIM];
   T gbody_pelvis[3], gbody_head[3], gquat_pelvis[4];
   T red[32];

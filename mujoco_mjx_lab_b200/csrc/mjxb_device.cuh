@@ -40,6 +40,10 @@ struct StepArgs {
   // deferred auto-reset: envs that finish an episode are queued per CTA and re-initialised in packed lockstep rounds after the
   // step rounds (a reset run inline would make the other 15 warps of its round wait for a whole extra pass)
   int* reset_list; int reset_stride;
+  // speculative auto-reset (small batches: every SM has idle warps): the CTA runs two warps per env, one steps it, its partner
+  // re-initialises it from its key at the same time (single_reset depends on the key alone), and the partner's result is stored only
+  // if the step finished the episode -- the reset no longer runs as a second, serialised pass of the pipeline
+  int spec_reset;
   int lockstep;          // CTA barriers keep the warps of an SM in the same code region (instruction-cache locality)
   int lockstep_group;    // warps per barrier group (0 = the whole CTA)
   // host-buffer pipeline: action / keys arrive in chunks of (1 << in_ready_shift) envs while the kernel already runs; the copy
@@ -485,6 +489,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
     for (int i = threadIdx.x; i < (int)(sizeof(DevModel) / 16); i += blockDim.x) dst[i] = src[i];
   }
   __shared__ int s_reset_count;
+  __shared__ int s_spec_done[32];
   if (threadIdx.x == 0) s_reset_count = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
@@ -498,8 +503,12 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
 
   const bool consuming = A.in_list != nullptr;
   const int n_items = consuming ? *reinterpret_cast<volatile int*>(A.in_count) : A.n_env;
-  const int n_rounds = (n_items + gridDim.x * nwarp - 1) / (gridDim.x * nwarp);
-  const bool defer = A.autoreset && A.reset_list != nullptr && A.mode == MODE_ENV_STEP;
+  const bool spec = SINGLE && A.spec_reset != 0 && A.autoreset && A.mode == MODE_ENV_STEP && !consuming;   // CTA-uniform
+  const int nslot = spec ? (nwarp >> 1) : nwarp;          // envs per CTA round
+  const int wslot = spec ? warp % nslot : warp;
+  const bool spec_partner = spec && warp >= nslot;        // this warp re-initialises env `wslot` speculatively
+  const int n_rounds = (n_items + gridDim.x * nslot - 1) / (gridDim.x * nslot);
+  const bool defer = A.autoreset && A.reset_list != nullptr && A.mode == MODE_ENV_STEP && !spec;
   int total_rounds = n_rounds, n_reset = 0;
   bool reset_phase = false;
   for (int round = 0;; round++) {
@@ -511,13 +520,13 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
       total_rounds += (n_reset + nwarp - 1) / nwarp;
       if (round == total_rounds) break;
     }
-    if (A.lockstep > 0) group_sync(warp, A.lockstep_group);
+    if (A.lockstep > 0 || spec) group_sync(warp, spec ? 0 : A.lockstep_group);
     // Warps without work in the last round (and envs that overflow the row tile) still run the whole pipeline -- on env 0 /
     // on a truncated row set -- with every global store suppressed, so that all warps of the CTA reach the same barriers.
     bool valid;
     int env;
     if (!reset_phase) {
-      const int item = (round * gridDim.x + blockIdx.x) * nwarp + warp;
+      const int item = (round * gridDim.x + blockIdx.x) * nslot + wslot;
       valid = item < n_items;
       env = valid ? (consuming ? A.in_list[item] : item) : (consuming ? A.in_list[0] : 0);
     } else {
@@ -527,12 +536,12 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
     }
     bool overflow = false, deferred = false;
     // ---------------------------------------------------------------- load state (lane d <-> qpos[d], qvel[d], ...)
-    int mode = reset_phase ? MODE_ENV_RESET : A.mode;
+    int mode = (reset_phase || spec_partner) ? MODE_ENV_RESET : A.mode;
     // Per-env values are NOT carried in registers across the pipeline (128 registers per thread, and the 24 KB of L1 left beside
     // 230 KB of shared memory cannot hold spills): they are published to shared memory here and re-read where they are used.
     float q = 0.0f, v = 0.0f, ws = 0.0f, ctrl = 0.0f, tm = 0.0f, aux = 0.0f;
     int status = consuming ? MJXB_STATUS_ROW_SPILL : 0;
-    if (A.in_ready != nullptr && !reset_phase) {  // wait for this env's chunk of action / keys (copy engine -> flag, L2-coherent)
+    if (A.in_ready != nullptr && !reset_phase) {   // (the speculative partner waits too: its key arrives with the chunk)  // wait for this env's chunk of action / keys (copy engine -> flag, L2-coherent)
       if (lane == 0) {
         const unsigned* flag = A.in_ready + (env >> A.in_ready_shift);
 #pragma unroll 1
@@ -1718,13 +1727,31 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
           } else if (src < 4 + nqj + C.nv) val = S.vec[VQVEL][6 + (src - 4 - nqj - 6)];
           else val = (src == od - 2) ? tg0 : tg1;
           if (flip > 0.5f) val *= cfg.obs_sign[o];
-          if (valid && !overflow && !deferred) A.obs[(size_t)env * od + o] = val;
+          if (spec_partner) S.J[o] = val;     // parked (J is dead by now); stored after the partner's verdict
+          else if (valid && !overflow && !deferred) A.obs[(size_t)env * od + o] = val;
         }
       }
       break;
       }  // pass
       (void)tgt_x; (void)tgt_y; (void)tgt_z;
     }  // nsteps
+    if (spec) {   // the stepping warp tells its partner whether the episode ended (CTA barrier: both warps of the pair are in this CTA)
+      if (!spec_partner && lane == 0) s_spec_done[wslot] = (valid && !overflow && deferred) ? 1 : 0;
+      __syncthreads();
+      if (spec_partner) {
+        const bool take = valid && !overflow && s_spec_done[wslot] != 0;
+        if (take) {
+          const int od = cfg.obs_dim;
+          for (int o = lane; o < od; o += 32) A.obs[(size_t)env * od + o] = S.J[o];
+          if (lane < C.nq) A.out.qpos[(size_t)env * C.nq + lane] = q;
+          if (lane < NV) { A.out.qvel[(size_t)env * NV + lane] = v; A.out.qacc_warmstart[(size_t)env * NV + lane] = ws; }
+          if (lane == 0) A.out.time[env] = tm;
+          if (lane < MJXB_AUX_DIM) A.out.aux[(size_t)env * MJXB_AUX_DIM + lane] = aux;
+        }
+        __syncwarp();
+        continue;
+      }
+    }
     if (!valid) continue;
     if (overflow) {  // leave the env untouched; the big-capacity pass redoes it from its inputs
       if (A.out_list != nullptr) {
@@ -1743,8 +1770,10 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
         A.reward[env] = out_reward; A.terminated[env] = out_term; A.truncated[env] = out_trunc;
         if (A.reset_mask) A.reset_mask[env] = 1;
         if (A.status) A.status[env] = status;
-        const int slot = atomicAdd(&s_reset_count, 1);
-        A.reset_list[(size_t)blockIdx.x * A.reset_stride + slot] = env;
+        if (!spec) {
+          const int slot = atomicAdd(&s_reset_count, 1);
+          A.reset_list[(size_t)blockIdx.x * A.reset_stride + slot] = env;
+        }
       }
       __syncwarp();
       continue;

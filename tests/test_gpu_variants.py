@@ -51,3 +51,32 @@ def test_cg_solver_apg_settings():
     model = helpers.load(overrides=dict(solver=modelc.SOLVER_CG, iterations=4, ls_iterations=4))
     dbg, ref = _compare(model, "lean", 600, tol_floor=1e-3)
     assert int(ref["solver_niter"].max()) == 4 and int(dbg["solver_niter"].max()) == 4
+
+
+def test_speculative_reset_is_bit_identical(model):
+    """Small batches (two warps per env fit on every SM) run the auto-reset speculatively beside the step (mjxb_abi.cu launch()):
+    same bits as the deferred-reset path, over steps that do reset envs, at sizes on both sides of the switch-over."""
+    import helpers
+    from mujoco_mjx_lab_b200 import _lib, training_utils
+    env_a = training_utils.load_model_and_create_env("", helpers.env_config(), model=model)
+    env_b = training_utils.load_model_and_create_env("", helpers.env_config(), model=model, flags=_lib.FLAG_NO_SPEC_RESET)
+    assert env_b[9].sys.lib.mjxb_model_flags(env_b[9].sys.handle) & _lib.FLAG_NO_SPEC_RESET
+    assert env_a[9].sys.lib.mjxb_model_flags(env_a[9].sys.handle) & _lib.FLAG_NO_SPEC_RESET == 0
+    for n in (1, 37, 1024, 1184, 1185):
+        keys = helpers.ppo_keys(n, n)
+        sa, oa = env_a[8](keys)
+        sb, ob = env_b[8](keys)
+        sa[1][: max(1, n // 7), 8] = 999.0                     # force truncations -> resets in the very first step
+        sb[1][: max(1, n // 7), 8] = 999.0
+        g = torch.Generator(device="cuda").manual_seed(n)
+        resets = 0
+        for t in range(12):
+            act = torch.randn(n, 21, device="cuda", generator=g) * (3.0 if t % 3 == 0 else 1.0)
+            rk = helpers.ppo_keys(100 + t, n)
+            sa, oa, ra, tea, tra = env_a[9].autoreset(sa, act, rk)
+            sb, ob, rb, teb, trb = env_b[9].autoreset(sb, act, rk)
+            resets += int(torch.maximum(tea, tra).sum())
+            assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(tea, teb) and torch.equal(tra, trb), (n, t)
+            assert torch.equal(sa[0].qpos, sb[0].qpos) and torch.equal(sa[0].qvel, sb[0].qvel) and torch.equal(sa[1], sb[1]), (n, t)
+            assert torch.equal(sa[0].qacc_warmstart, sb[0].qacc_warmstart) and torch.equal(sa[0].time, sb[0].time), (n, t)
+        assert resets >= max(1, n // 7)
