@@ -127,9 +127,13 @@ class APGTrainer:
             act = _policy_apply(self.params, torch.nan_to_num(x, nan=0.0, posinf=1e6, neginf=-1e6))
             state, _, r, te, tr = diff_step(self.sys, state, act)
             done = torch.maximum(te, tr)
-            # (an env that already finished contributes nothing; it keeps stepping without reset as in the reference, and a body that
-            #  has numerically diverged AFTER its episode ended must not turn 0 * nan into nan)
-            r = torch.where(disc > 0, r, torch.zeros_like(r))
+            # Guards the reference does not have (its trainer stops on a non-finite loss, train_apg.py:278): with the 4-iteration CG of
+            # train_apg.py:101-105 a few fallen bodies per thousand diverge numerically within ~100 steps (the CPU restatement of mjx.step
+            # does the same, tools/apg_stability_probe.py). An env that has already finished contributes nothing (0 * nan must stay 0),
+            # and an env whose reward is non-finite or absurd is treated as finished at that step.
+            diverged = (~torch.isfinite(r)) | (r.abs() > 1e3)
+            r = torch.where((disc > 0) & ~diverged, r, torch.zeros_like(r))
+            done = torch.maximum(done, diverged.float())
             acc = acc + disc * r
             disc = disc * self.cfg.gamma * (1.0 - done)
             obs_traj.append(obs.detach())

@@ -214,14 +214,15 @@ int launch(const mjxb_model* m, const StepArgs& args_in, bool dbg, cudaStream_t 
   const bool ls = m->host.ls_exact != 0 && m->host.solver == 2;  // fast instantiation: Newton + exact line search; else the general one
 #define MJXB_LAUNCH(CAPv, CCv, Wv, G, B, SM)                                                                                   \
   do {                                                                                                                        \
-    if (dbg && ls) mjxb_step_kernel<true, CAPv, CCv, Wv, true><<<G, B, SM, stream>>>(m->dev, m->dev_pp, args);                  \
-    else if (dbg) mjxb_step_kernel<true, CAPv, CCv, Wv, false><<<G, B, SM, stream>>>(m->dev, m->dev_pp, args);                  \
-    else if (ls) mjxb_step_kernel<false, CAPv, CCv, Wv, true><<<G, B, SM, stream>>>(m->dev, m->dev_pp, args);                   \
-    else mjxb_step_kernel<false, CAPv, CCv, Wv, false><<<G, B, SM, stream>>>(m->dev, m->dev_pp, args);                          \
+    if (dbg && ls) launch_pdl(mjxb_step_kernel<true, CAPv, CCv, Wv, true>, dim3(G), dim3(B), SM, stream, (const DevModel*)m->dev, (const PairParam*)m->dev_pp, args);   \
+    else if (dbg) launch_pdl(mjxb_step_kernel<true, CAPv, CCv, Wv, false>, dim3(G), dim3(B), SM, stream, (const DevModel*)m->dev, (const PairParam*)m->dev_pp, args);   \
+    else if (ls) launch_pdl(mjxb_step_kernel<false, CAPv, CCv, Wv, true>, dim3(G), dim3(B), SM, stream, (const DevModel*)m->dev, (const PairParam*)m->dev_pp, args);    \
+    else launch_pdl(mjxb_step_kernel<false, CAPv, CCv, Wv, false>, dim3(G), dim3(B), SM, stream, (const DevModel*)m->dev, (const PairParam*)m->dev_pp, args);           \
   } while (0)
   // hot instantiation: one step per launch, Newton + exact line search, resets deferred (or none requested)
   const bool single = !dbg && ls && args.nsteps == 1 && (!(args.mode == MODE_ENV_STEP && args.autoreset) || args.reset_list != nullptr);
-  if (single) mjxb_step_kernel<false, CAP_MAIN, MAXCC_MAIN, WARPS_MAIN, true, true><<<grid, warps * 32, smem_main, stream>>>(m->dev, m->dev_pp, args);
+  if (single) launch_pdl(mjxb_step_kernel<false, CAP_MAIN, MAXCC_MAIN, WARPS_MAIN, true, true>, dim3(grid), dim3(warps * 32), smem_main, stream,
+                         (const DevModel*)m->dev, (const PairParam*)m->dev_pp, args);
   else MJXB_LAUNCH(CAP_MAIN, MAXCC_MAIN, WARPS_MAIN, grid, warps * 32, smem_main);
   g_mjxb_launches += 3;   // main tier + the two overflow tiers below (each leaves at once when its list is empty)
   cudaError_t e = cudaGetLastError();
@@ -268,6 +269,10 @@ int model_view(const mjxb_model* m, ModelView* out) {
 }
 int model_scratch(const mjxb_model* m, cudaStream_t stream, int n_env, int** buf, int* cap) { return scratch_for(m, stream, n_env, buf, cap); }
 int report_cuda_error(cudaError_t e, const char* what) { return cuda_fail(e, what); }
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("MJXB_PDL"); return e ? atoi(e) != 0 : true; }();
+  return on;
+}
 }  // namespace mjxb
 
 extern "C" {

@@ -24,6 +24,7 @@ struct VjpArgs {
 template <int CAP, int MAXCC>
 __global__ void __launch_bounds__(256, 1) step_vjp_kernel(const DevModel* __restrict__ gmodel, const PairParam* __restrict__ pair_param, VjpArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  pdl_prologue();
   if (A.in_list != nullptr && *reinterpret_cast<volatile int*>(A.in_count) == 0) return;   // empty overflow list: leave at once
   DevModel& C = *reinterpret_cast<DevModel*>(smem_raw);
   {
@@ -148,11 +149,11 @@ int mjxb_step_vjp(const mjxb_model* m, int32_t n_env, mjxb_state in, const float
     A.in_count = nullptr; A.in_list = nullptr; A.in_done = nullptr; A.out_count = buf; A.out_list = buf + 4;
     int grid = (n_env + g.warps - 1) / g.warps;
     if (grid > mv.num_sms) grid = mv.num_sms;
-    step_vjp_kernel<VJP_CAP, VJP_MAXCC><<<grid, g.warps * 32, g.smem, stream>>>(mv.dev, mv.dev_pp, A);
+    launch_pdl(step_vjp_kernel<VJP_CAP, VJP_MAXCC>, dim3(grid), dim3(g.warps * 32), g.smem, stream, mv.dev, mv.dev_pp, A);
     A.in_count = buf; A.in_done = buf + 1; A.in_list = buf + 4; A.out_count = nullptr; A.out_list = nullptr;
     int gridb = (n_env + g.warps_big - 1) / g.warps_big;
     if (gridb > mv.num_sms) gridb = mv.num_sms;
-    step_vjp_kernel<CAP_BIG, MAXCC_BIG><<<gridb, g.warps_big * 32, g.smem_big, stream>>>(mv.dev, mv.dev_pp, A);
+    launch_pdl(step_vjp_kernel<CAP_BIG, MAXCC_BIG>, dim3(gridb), dim3(g.warps_big * 32), g.smem_big, stream, mv.dev, mv.dev_pp, A);
     g_mjxb_launches += 2;
     e = cudaGetLastError();
     if (e != cudaSuccess) rc = report_cuda_error(e, "step_vjp_kernel launch");

@@ -480,6 +480,9 @@ template <bool DBG, int CAP, int MAXCC, int MAXW, bool LS_EXACT, bool SINGLE = f
 __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel* __restrict__ gmodel, const PairParam* __restrict__ pair_param,
                                                             StepArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  // programmatic dependent launch: let the successor be staged, then wait for the predecessor's results (no-ops in a plain launch)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   // an overflow tier whose input list is empty (the common case) leaves before it touches shared memory
   if (A.in_list != nullptr && *reinterpret_cast<volatile int*>(A.in_count) == 0) return;
   DevModel& C = *reinterpret_cast<DevModel*>(smem_raw);

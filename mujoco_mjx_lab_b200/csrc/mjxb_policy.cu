@@ -18,8 +18,7 @@
 #include <stdio.h>
 
 #include "mjxb.h"
-
-extern std::atomic<long long> g_mjxb_launches;
+#include "mjxb_internal.h"
 
 namespace mjxbp {
 
@@ -97,6 +96,7 @@ struct PolicyArgs {
 
 __global__ void __launch_bounds__(kThreads, 1) policy_act_kernel(PolicyArgs P) {
   extern __shared__ __align__(1024) unsigned char smem[];
+  mjxb::pdl_prologue();   // staged behind the previous env step's kernels; waits here until their observations are visible
   unsigned char* sA = smem;
   unsigned char* sW = smem + kABytes;
   float* sBias2 = reinterpret_cast<float*>(smem + kABytes + kWBytes);   // [2][kHid]: layer l+1 is staged while layer l's epilogue reads
@@ -413,7 +413,7 @@ int mjxb_policy_act(int32_t n_env, int32_t obs_dim, int32_t act_dim, const float
   P.log_std = log_std; P.eps = eps; P.act = act; P.logp = logp; P.mean = mean; P.error = error_flag;
   const int grid = (n_env + mjxbp::kTile - 1) / mjxbp::kTile;
   g_mjxb_launches++;
-  mjxbp::policy_act_kernel<<<grid, mjxbp::kThreads, mjxbp::kSmemBytes, (cudaStream_t)stream>>>(P);
+  mjxb::launch_pdl(mjxbp::policy_act_kernel, dim3(grid), dim3(mjxbp::kThreads), (size_t)mjxbp::kSmemBytes, (cudaStream_t)stream, P);
   return cudaGetLastError() == cudaSuccess ? MJXB_OK : MJXB_ECUDA;
 }
 
