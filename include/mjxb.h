@@ -200,6 +200,19 @@ int mjxb_policy_act(int32_t n_env, int32_t obs_dim, int32_t act_dim, const float
  * arrays (y == NULL: plain linear layer, dz is not written and db += column sums of dy). db must be zeroed by the caller. */
 int mjxb_tanh_bwd_colsum(int32_t n, int32_t c, const float* dy, const float* y, float* dz, float* db_zeroed, void* stream);
 
+/* Losses of one PPO minibatch and their gradients in two launches (reference train_ppo.py:204-252): logp = Gaussian log-density of
+ * action under (mean, exp(log_std)); ratio = exp(logp - old_logp); adv_n = (adv - mean(adv)) / (std(adv) + 1e-8) over the minibatch;
+ * loss = mean(-min(ratio adv_n, clip(ratio, 1 +- clip_eps) adv_n)) - ent_coef * entropy(log_std). Writes d loss / d mean [n, act_dim],
+ * d loss / d log_std [act_dim] and the loss (loss_out[0]); scratch4 is 4 floats of device scratch. All pointers are device pointers. */
+int mjxb_ppo_loss(int32_t n, int32_t act_dim, const float* mean, const float* log_std, const float* action, const float* old_logp,
+                  const float* adv, float clip_eps, float ent_coef, float* scratch4, float* g_mean, float* g_log_std, float* loss_out,
+                  void* stream);
+/* Adam (optax.adam semantics: bias-corrected moments, eps outside the square root) over one flat parameter / gradient buffer of n floats:
+ * elements [0, split) use lr0, the rest lr1; grad is multiplied by grad_scale first (1 / world size after an all-reduce sum);
+ * *step_dev (device float, 0 at the start) counts the updates, so the call can be replayed from a CUDA graph. */
+int mjxb_adam(int32_t n, int32_t split, float* param, const float* grad, float* m, float* v, float* step_dev, float lr0, float lr1,
+              float b1, float b2, float eps, float grad_scale, void* stream);
+
 /* Generalised advantage estimation over a rollout (reference train_ppo.py:171-202): delta_t = r_t + gamma v_{t+1} (1 - terminated_t) - v_t,
  * adv_t = delta_t + gamma lam (1 - max(terminated_t, truncated_t)) adv_{t+1}, ret_t = adv_t + v_t. reward / terminated / truncated /
  * advantage / ret are [rollout_length, n_env], value is [rollout_length + 1, n_env]; device pointers, one launch. */

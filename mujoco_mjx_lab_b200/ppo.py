@@ -93,6 +93,47 @@ def gaussian_logprob(mean, log_std, action):  # reference train_ppo.py:121-126
     return -0.5 * torch.sum((action - mean) ** 2 / var + 2.0 * log_std + math.log(2.0 * math.pi), dim=-1)
 
 
+class _PPOLoss(torch.autograd.Function):
+    """Policy loss of one minibatch (reference train_ppo.py:204-232) with its gradients produced by the forward launches
+    (include/mjxb.h mjxb_ppo_loss): replaces ~45 elementwise / reduction launches of the autograd chain by two."""
+
+    @staticmethod
+    def forward(ctx, mean, log_std, action, old_logp, adv, clip_eps: float, ent_coef: float):
+        import ctypes as C
+        from . import _lib
+        mean, action, old_logp, adv = mean.contiguous(), action.contiguous(), old_logp.contiguous(), adv.contiguous()
+        n, a = mean.shape
+        g_mean, g_ls = torch.empty_like(mean), torch.empty_like(log_std)
+        scratch = torch.empty(5, dtype=torch.float32, device=mean.device)          # [0:4] statistics, [4] the loss
+        _lib.check(_lib.lib().mjxb_ppo_loss(n, a, mean.data_ptr(), log_std.data_ptr(), action.data_ptr(), old_logp.data_ptr(), adv.data_ptr(),
+                                            float(clip_eps), float(ent_coef), scratch.data_ptr(), g_mean.data_ptr(), g_ls.data_ptr(),
+                                            scratch[4:].data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "mjxb_ppo_loss")
+        ctx.save_for_backward(g_mean, g_ls)
+        return scratch[4]
+
+    @staticmethod
+    def backward(ctx, g):
+        g_mean, g_ls = ctx.saved_tensors
+        return g_mean * g, g_ls * g, None, None, None, None, None
+
+
+class _FlatAdam:
+    """optax.adam / torch.optim.Adam over ONE flat parameter / gradient buffer (include/mjxb.h mjxb_adam): two launches per step, the
+    step counter lives on the device (CUDA-graph replayable); [0, split) uses lr0, the rest lr1."""
+
+    def __init__(self, flat_p, flat_g, split: int, lr0: float, lr1: float, eps: float = 1e-8):
+        self.p, self.g, self.split, self.lr0, self.lr1, self.eps = flat_p, flat_g, split, lr0, lr1, eps
+        self.m, self.v = torch.zeros_like(flat_p), torch.zeros_like(flat_p)
+        self.step_dev = torch.zeros(1, dtype=torch.float32, device=flat_p.device)
+
+    def step(self, grad_scale: float = 1.0):
+        import ctypes as C
+        from . import _lib
+        _lib.check(_lib.lib().mjxb_adam(self.p.numel(), self.split, self.p.data_ptr(), self.g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                                        self.step_dev.data_ptr(), self.lr0, self.lr1, 0.9, 0.999, self.eps, float(grad_scale),
+                                        C.c_void_p(torch.cuda.current_stream().cuda_stream)), "mjxb_adam")
+
+
 @dataclass
 class RMS:  # reference src/training_utils.py:20-56
     mean: torch.Tensor
@@ -135,7 +176,7 @@ class RMS:  # reference src/training_utils.py:20-56
 
 class PPOTrainer:
     def __init__(self, cfg: PPOConfig, v_reset, v_step, num_envs_local: int, seed: int = 42, use_cuda_graph: bool = True,
-                 use_fused_policy: bool = True):
+                 use_fused_policy: bool = True, use_fused_learner: bool = True):
         self.cfg, self.v_reset, self.v_step = cfg, v_reset, v_step
         self.sys = v_step.sys
         self.dev = self.sys.device
@@ -149,8 +190,27 @@ class PPOTrainer:
         self.policy = _mlp_params(od, cfg.policy_hidden_layer_specs, nu, gen, self.dev)
         self.log_std = torch.full((nu,), float(cfg.log_std_init), device=self.dev, requires_grad=True)
         self.value = _mlp_params(od, cfg.value_hidden_layer_specs, 1, gen, self.dev)
-        self.opt_p = torch.optim.Adam(self.policy + [self.log_std], lr=cfg.lr_policy, eps=1e-8, capturable=True)
-        self.opt_v = torch.optim.Adam(self.value, lr=cfg.lr_value, eps=1e-8, capturable=True)
+        self.fused_learner = bool(use_fused_learner) and self.dev.type == "cuda" and nu <= 32
+        if self.fused_learner:
+            # every parameter is a view into ONE flat buffer and its .grad a view into one flat gradient buffer: autograd accumulates
+            # in place, the NCCL all-reduce runs on the flat gradient without a flatten / unflatten pass, Adam is one kernel
+            allp = self.policy + [self.log_std] + self.value
+            n_pol = sum(p.numel() for p in self.policy) + self.log_std.numel()
+            self.flat_p = torch.cat([p.detach().reshape(-1) for p in allp]).contiguous()
+            self.flat_g = torch.zeros_like(self.flat_p)
+            views, o = [], 0
+            for p in allp:
+                v = self.flat_p[o:o + p.numel()].view(p.shape).detach().requires_grad_()
+                v.grad = self.flat_g[o:o + p.numel()].view(p.shape)
+                views.append(v)
+                o += p.numel()
+            npol = len(self.policy)
+            self.policy, self.log_std, self.value = views[:npol], views[npol], views[npol + 1:]
+            self.opt = _FlatAdam(self.flat_p, self.flat_g, n_pol, cfg.lr_policy, cfg.lr_value)
+            self.opt_p = self.opt_v = None
+        else:
+            self.opt_p = torch.optim.Adam(self.policy + [self.log_std], lr=cfg.lr_policy, eps=1e-8, capturable=True)
+            self.opt_v = torch.optim.Adam(self.value, lr=cfg.lr_value, eps=1e-8, capturable=True)
         self.rms = RMS.create(od, self.dev)
         self.gen = torch.Generator(device=self.dev).manual_seed(seed + 1000 * (self.rank + 1))
         torch.cuda.manual_seed(seed + 7919 * (self.rank + 1))
@@ -268,20 +328,37 @@ class PPOTrainer:
             adv[t] = carry
         return adv, adv + values[:-1]
 
+    def _zero_grads(self):
+        if self.fused_learner:
+            self.flat_g.zero_()
+        else:
+            self.opt_p.zero_grad(set_to_none=True)
+            self.opt_v.zero_grad(set_to_none=True)
+
+    def _opt_step(self):
+        """Adam on both networks; sharded runs divide the all-reduced gradient sum by the world size first."""
+        if self.fused_learner:
+            self.opt.step(1.0 / self.world)
+        else:
+            self.opt_p.step()
+            self.opt_v.step()
+
     def _minibatch_fb(self, obs_f, act_f, logp_f, ret_f, adv_f, idx, zero: bool):
         """Losses of one minibatch (train_ppo.py:204-252) and their gradients."""
         cfg = self.cfg
         o, a, olp, r_, ad = obs_f[idx], act_f[idx], logp_f[idx], ret_f[idx], adv_f[idx]
-        mean = _mlp_apply(self.policy, o, self.nh_p)
-        logp = gaussian_logprob(mean, self.log_std, a)
-        ratio = torch.exp(logp - olp)
-        ad_n = (ad - ad.mean()) / (ad.std(unbiased=False) + 1e-8)
-        loss_p = -torch.minimum(ratio * ad_n, torch.clamp(ratio, 1 - cfg.clip_eps, 1 + cfg.clip_eps) * ad_n).mean()
-        entropy = 0.5 * torch.sum(1.0 + math.log(2.0 * math.pi) + 2.0 * self.log_std) / a.shape[-1]
-        loss = loss_p - cfg.ent_coef * entropy
         if zero:
-            self.opt_p.zero_grad(set_to_none=True)
-            self.opt_v.zero_grad(set_to_none=True)
+            self._zero_grads()
+        mean = _mlp_apply(self.policy, o, self.nh_p)
+        if self.fused_learner:
+            loss = _PPOLoss.apply(mean, self.log_std, a, olp, ad, cfg.clip_eps, cfg.ent_coef)
+        else:
+            logp = gaussian_logprob(mean, self.log_std, a)
+            ratio = torch.exp(logp - olp)
+            ad_n = (ad - ad.mean()) / (ad.std(unbiased=False) + 1e-8)
+            loss_p = -torch.minimum(ratio * ad_n, torch.clamp(ratio, 1 - cfg.clip_eps, 1 + cfg.clip_eps) * ad_n).mean()
+            entropy = 0.5 * torch.sum(1.0 + math.log(2.0 * math.pi) + 2.0 * self.log_std) / a.shape[-1]
+            loss = loss_p - cfg.ent_coef * entropy
         loss.backward()
         v = _mlp_apply(self.value, o, self.nh_v).squeeze(-1)
         loss_v = torch.mean((v - r_) ** 2)
@@ -294,27 +371,31 @@ class PPOTrainer:
         If this NCCL build refuses stream capture the collective stays eager between two graphs (u["st"] is then the second half)."""
         u = self.upd
         params = self.policy + [self.log_std] + self.value
+        if self.fused_learner:
+            u["flat"] = self.flat_g
         torch.cuda.synchronize()
 
         def unflatten_and_step():
+            if self.fused_learner:                                      # the collective ran on the flat gradient buffer itself
+                self._opt_step()
+                return
             o = 0
             for p in params:
                 p.grad.copy_(u["flat"][o:o + p.numel()].view_as(p.grad) / self.world)
                 o += p.numel()
-            self.opt_p.step()
-            self.opt_v.step()
+            self._opt_step()
 
         def capture(fused_collective: bool):
-            self.opt_p.zero_grad(set_to_none=True)
-            self.opt_v.zero_grad(set_to_none=True)
+            if not self.fused_learner:
+                self._zero_grads()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self._minibatch_fb(u["obs"], u["act"], u["logp"], u["ret"], u["adv"], u["idx"], zero=False)
+                self._minibatch_fb(u["obs"], u["act"], u["logp"], u["ret"], u["adv"], u["idx"], zero=self.fused_learner)
                 if self.world == 1:
-                    self.opt_p.step()
-                    self.opt_v.step()
+                    self._opt_step()
                 else:
-                    u["flat"].copy_(torch.cat([p.grad.reshape(-1) for p in params]))
+                    if not self.fused_learner:
+                        u["flat"].copy_(torch.cat([p.grad.reshape(-1) for p in params]))
                     if fused_collective:
                         dist.all_reduce(u["flat"])
                         unflatten_and_step()
@@ -344,6 +425,9 @@ class PPOTrainer:
 
     def _allreduce_grads(self, params):
         if self.world == 1:
+            return
+        if self.fused_learner:                 # sum over ranks; _opt_step divides by the world size
+            dist.all_reduce(self.flat_g)
             return
         flat = torch.cat([p.grad.reshape(-1) for p in params])
         dist.all_reduce(flat)
@@ -389,16 +473,14 @@ class PPOTrainer:
                 if not self.use_graph:
                     self._minibatch_fb(obs_f, act_f, logp_f, ret_f, adv_f, idx, zero=True)
                     self._allreduce_grads(self.policy + [self.log_std] + self.value)
-                    self.opt_p.step()
-                    self.opt_v.step()
+                    self._opt_step()
                     continue
                 u = self.upd
                 u["idx"].copy_(idx)
                 if u["eager_steps"] < 3:        # warm-up on real minibatches (cuBLAS workspaces, Adam state) before the capture
                     self._minibatch_fb(u["obs"], u["act"], u["logp"], u["ret"], u["adv"], u["idx"], zero=True)
                     self._allreduce_grads(self.policy + [self.log_std] + self.value)
-                    self.opt_p.step()
-                    self.opt_v.step()
+                    self._opt_step()
                     u["eager_steps"] += 1
                     continue
                 if u["fb"] is None:

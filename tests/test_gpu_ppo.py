@@ -81,3 +81,78 @@ def test_linear_act_backward_matches_autograd():
         torch.testing.assert_close(gx, rx, rtol=1e-3, atol=1e-3)
         torch.testing.assert_close(gw, rw, rtol=1e-3, atol=5e-2)        # TF32 products summed over n rows
         torch.testing.assert_close(gb, rb, rtol=1e-4, atol=1e-2)
+
+
+def test_fused_ppo_loss_matches_autograd():
+    """mjxb_ppo_loss (loss + gradients in two launches) against the torch autograd chain it replaces (reference train_ppo.py:204-232)."""
+    import math
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for n, a in [(65536, 21), (1000, 21), (257, 5)]:
+        mean = (torch.randn(n, a, device="cuda", generator=g) * 0.3).requires_grad_()
+        log_std = (torch.randn(a, device="cuda", generator=g) * 0.2).requires_grad_()
+        act = mean.detach() + torch.exp(log_std.detach()) * torch.randn(n, a, device="cuda", generator=g)
+        olp = ppo_mod.gaussian_logprob(mean.detach() + 0.05 * torch.randn(n, a, device="cuda", generator=g), log_std.detach(), act)
+        adv = torch.randn(n, device="cuda", generator=g) * 3 + 0.5
+        loss = ppo_mod._PPOLoss.apply(mean, log_std, act, olp, adv, 0.2, 0.01)
+        gm, gl = torch.autograd.grad(loss, (mean, log_std))
+        logp = ppo_mod.gaussian_logprob(mean, log_std, act)
+        ratio = torch.exp(logp - olp)
+        ad_n = (adv - adv.mean()) / (adv.std(unbiased=False) + 1e-8)
+        ref = -torch.minimum(ratio * ad_n, torch.clamp(ratio, 0.8, 1.2) * ad_n).mean() - 0.01 * 0.5 * torch.sum(1.0 + math.log(2.0 * math.pi) + 2.0 * log_std) / a
+        rm, rl = torch.autograd.grad(ref, (mean, log_std))
+        assert (ratio < 0.8).any() and (ratio > 1.2).any()                        # both clip branches are exercised
+        torch.testing.assert_close(loss, ref, rtol=1e-4, atol=1e-5)
+        # a sample whose ratio sits within float32 rounding of a clip boundary may take the other branch (zero vs non-zero gradient)
+        edge = ((ratio - 0.8).abs() < 1e-5) | ((ratio - 1.2).abs() < 1e-5)
+        assert int(edge.sum()) <= 4
+        keep = ~edge.detach()
+        torch.testing.assert_close(gm[keep], rm[keep], rtol=1e-3, atol=1e-8)
+        if not bool(edge.any()):
+            torch.testing.assert_close(gl, rl, rtol=1e-3, atol=1e-6)
+        else:
+            torch.testing.assert_close(gl, rl, rtol=2e-2, atol=1e-4)
+
+
+def test_flat_adam_matches_torch_adam():
+    g = torch.Generator(device="cuda").manual_seed(4)
+    n, split = 5000, 3000
+    p0 = torch.randn(n, device="cuda", generator=g)
+    pa, pb = p0.clone(), p0.clone().requires_grad_()
+    ga = torch.zeros(n, device="cuda")
+    opt_a = ppo_mod._FlatAdam(pa, ga, split, 3e-4, 1e-3)
+    opt_b = torch.optim.Adam([{"params": [pb]}], lr=1.0, eps=1e-8)           # per-element lr applied through the gradient below is not
+    lr = torch.cat([torch.full((split,), 3e-4), torch.full((n - split,), 1e-3)]).cuda()   # possible: emulate with two tensors instead
+    pb1, pb2 = p0[:split].clone().requires_grad_(), p0[split:].clone().requires_grad_()
+    o1, o2 = torch.optim.Adam([pb1], lr=3e-4, eps=1e-8), torch.optim.Adam([pb2], lr=1e-3, eps=1e-8)
+    for t in range(20):
+        grad = torch.randn(n, device="cuda", generator=g) * (1.0 + t)
+        ga.copy_(grad * 2.0)
+        opt_a.step(0.5)                                                       # grad_scale: 1 / world size
+        pb1.grad, pb2.grad = grad[:split].clone(), grad[split:].clone()
+        o1.step(); o2.step()
+    torch.testing.assert_close(pa[:split], pb1.detach(), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(pa[split:], pb2.detach(), rtol=1e-5, atol=1e-6)
+    assert float(opt_a.step_dev) == 20.0
+
+
+def test_fused_learner_equals_torch_learner(env):
+    """Same rollouts, same minibatch permutations: flat-buffer parameters + fused loss + flat Adam give the parameters of the torch
+    autograd / torch.optim.Adam learner."""
+    cfg = PPOConfig()
+    cfg.rollout_length, cfg.minibatch_size, cfg.epochs = 16, 512, 4
+    cfg.env_config = helpers.env_config()
+    a = ppo_mod.PPOTrainer(cfg, env[8], env[9], 128, seed=5, use_cuda_graph=False, use_fused_learner=True)
+    b = ppo_mod.PPOTrainer(cfg, env[8], env[9], 128, seed=5, use_cuda_graph=False, use_fused_learner=False)
+    assert a.fused_learner and not b.fused_learner
+    for pa, pb in zip(a.policy + [a.log_std] + a.value, b.policy + [b.log_std] + b.value):
+        assert torch.equal(pa, pb)
+
+    def copy_rollout():
+        for name in ("obs_traj", "act_traj", "logp_traj", "r_traj", "term_traj", "trunc_traj", "obs"):
+            getattr(b, name).copy_(getattr(a, name))
+    b.collect_rollout = copy_rollout
+    for _ in range(2):
+        a.iteration()
+        b.iteration()
+        for pa, pb in zip(a.policy + [a.log_std] + a.value, b.policy + [b.log_std] + b.value):
+            torch.testing.assert_close(pa, pb, rtol=2e-3, atol=2e-4)
