@@ -95,7 +95,8 @@ def _policy_apply(params, x):
 
 
 class APGTrainer:
-    def __init__(self, cfg: APGConfig, v_reset, v_step, batch_size_local: int, env_cfg=None, seed: int = 0, output_scale: float = 1.0):
+    def __init__(self, cfg: APGConfig, v_reset, v_step, batch_size_local: int, env_cfg=None, seed: int = 0, output_scale: float = 1.0,
+                 use_cuda_graph: bool = True):
         self.cfg, self.v_reset, self.v_step = cfg, v_reset, v_step
         self.sys = v_step.sys
         self.dev = self.sys.device
@@ -106,14 +107,17 @@ class APGTrainer:
         self.obs_dim = self.sys.nq + self.sys.nv                                  # reference train_apg.py:119
         gen = torch.Generator(device=self.dev).manual_seed(seed)
         self.params = _policy_params(self.obs_dim, cfg.hidden_size, cfg.hidden_depth, self.sys.nu, gen, self.dev, output_scale)
-        self.opt = torch.optim.Adam(self.params, lr=cfg.lr, eps=1e-8)
+        self.opt = torch.optim.Adam(self.params, lr=cfg.lr, eps=1e-8, capturable=True)
+        self.use_graph, self.graph, self.eager_steps = bool(use_cuda_graph), None, 0
+        self.keys_buf = torch.zeros(self.n, 2, dtype=torch.int32, device=self.dev)
+        self.norm_flag = torch.zeros((), dtype=torch.bool, device=self.dev)       # train_apg.py:171-175 jnp.where(use_norm, ...)
         self.obs_mean = torch.zeros(self.obs_dim, device=self.dev)
         self.obs_var = torch.ones(self.obs_dim, device=self.dev)
         self.obs_count = 1e-4
         self.step_no = 0
         self.seed = seed
 
-    def rollout_return(self, keys, use_norm: bool):
+    def rollout_return(self, keys, use_norm=None):
         """reference train_apg.py:161-190. Returns (mean discounted return, obs trajectory, mean reward)."""
         state, _ = self.v_reset(keys)
         n = self.n
@@ -123,7 +127,7 @@ class APGTrainer:
         for _ in range(self.H):
             d, aux = state
             obs = torch.cat([d.qpos, d.qvel], dim=1)
-            x = torch.clamp((obs - self.obs_mean) / (torch.sqrt(self.obs_var) + 1e-8), -10.0, 10.0) if use_norm else obs
+            x = torch.where(self.norm_flag, torch.clamp((obs - self.obs_mean) / (torch.sqrt(self.obs_var) + 1e-8), -10.0, 10.0), obs)
             act = _policy_apply(self.params, torch.nan_to_num(x, nan=0.0, posinf=1e6, neginf=-1e6))
             state, _, r, te, tr = diff_step(self.sys, state, act)
             done = torch.maximum(te, tr)
@@ -140,16 +144,18 @@ class APGTrainer:
             r_sum = r_sum + r.detach().mean()
         return acc.mean(), torch.stack(obs_traj), r_sum / self.H
 
-    def update(self, time_split: bool = False) -> Dict[str, float]:
-        """reference train_apg.py:197-209 + :253-262: one optimisation step (value_and_grad of -return, clip 0.3, Adam)."""
-        keys = torch.from_numpy(parallel.rank_keys(self.seed + 1 + self.step_no, self.rank, self.n).view(np.int32)).to(self.dev)
-        use_norm = self.cfg.normalize_observations and self.step_no >= 100                    # warm-up without normalisation (:238)
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-        self.opt.zero_grad(set_to_none=True)
-        ev[0].record()
-        ret, obs_traj, mean_reward = self.rollout_return(keys, use_norm)
+    def _fwd_bwd_step(self, ev=None):
+        """One optimisation step on self.keys_buf (everything on the current stream, capturable): value_and_grad of -return through the
+        rollout, gradient all-reduce when sharded, clip_by_global_norm(0.3), Adam. Returns loss / statistics as device tensors."""
+        for p in self.params:
+            if p.grad is not None:
+                p.grad.zero_()
+        if ev:
+            ev[0].record()
+        ret, obs_traj, mean_reward = self.rollout_return(self.keys_buf)
         loss = -ret
-        ev[1].record()
+        if ev:
+            ev[1].record()
         loss.backward()
         if self.world > 1:
             flat = torch.cat([p.grad.reshape(-1) for p in self.params])
@@ -159,20 +165,57 @@ class APGTrainer:
             for p in self.params:
                 p.grad.copy_(flat[o:o + p.numel()].view_as(p.grad))
                 o += p.numel()
-        grad_norm = torch.nn.utils.clip_grad_norm_(self.params, 0.3)                        # optax.clip_by_global_norm(0.3)
+        grad_norm = torch.nn.utils.clip_grad_norm_(self.params, 0.3, foreach=True)          # optax.clip_by_global_norm(0.3)
         self.opt.step()
-        ev[2].record()
-        if self.cfg.normalize_observations and self.step_no % 10 == 0:                      # :289-291
+        if ev:
+            ev[2].record()
+        return loss.detach(), mean_reward, grad_norm.detach(), obs_traj
+
+    def update(self) -> Dict[str, float]:
+        """reference train_apg.py:197-209 + :253-262: one optimisation step. After two eager steps the whole update -- 128 policy /
+        step launches forward, the reverse sweep through mjxb_step_vjp, clip, Adam -- is captured once and replayed as ONE CUDA graph
+        (the eager loop is bound by ~2500 launch dispatches per update, not by the GPU)."""
+        keys = torch.from_numpy(parallel.rank_keys(self.seed + 1 + self.step_no, self.rank, self.n).view(np.int32)).to(self.dev)
+        self.keys_buf.copy_(keys)
+        self.norm_flag.fill_(bool(self.cfg.normalize_observations and self.step_no >= 100))   # warm-up without normalisation (:238)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if not self.use_graph or self.eager_steps < 2:
+            t0.record()
+            self._out = self._fwd_bwd_step(ev)
+            t1.record()
+            self.eager_steps += 1
+            split = True
+        else:
+            if self.graph is None:
+                s = torch.cuda.Stream(device=self.dev)
+                s.wait_stream(torch.cuda.current_stream())
+                self.sys.reserve(self.n, s)                              # launch scratch of the capture stream (include/mjxb.h)
+                torch.cuda.synchronize()
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph, stream=s):
+                    self._out = self._fwd_bwd_step(None)
+            t0.record()
+            self.graph.replay()
+            t1.record()
+            split = False
+        loss, mean_reward, grad_norm, obs_traj = self._out
+        if self.cfg.normalize_observations and self.step_no % 10 == 0:                      # :289-291 (in place: the graph reads these)
             x = obs_traj.reshape(-1, self.obs_dim).double()
+            x = torch.nan_to_num(x, nan=0.0, posinf=0.0, neginf=0.0)
             bm, bv, bn = x.mean(0), x.var(0, unbiased=False), float(x.shape[0])
             delta, tot = bm - self.obs_mean.double(), self.obs_count + bn
             mean = self.obs_mean.double() + delta * bn / tot
             m2 = self.obs_var.double() * self.obs_count + bv * bn + delta * delta * self.obs_count * bn / tot
-            self.obs_mean, self.obs_var, self.obs_count = mean.float(), torch.clamp_min(m2 / tot, 1e-4).float(), tot
+            self.obs_mean.copy_(mean.float())
+            self.obs_var.copy_(torch.clamp_min(m2 / tot, 1e-4).float())
+            self.obs_count = tot
         self.step_no += 1
         torch.cuda.synchronize()
-        out = {"loss": float(loss.detach()), "mean_reward": float(mean_reward), "grad_norm": float(grad_norm),
-               "forward_ms": ev[0].elapsed_time(ev[1]), "backward_ms": ev[1].elapsed_time(ev[2]), "update_ms": ev[0].elapsed_time(ev[2])}
+        out = {"loss": float(loss), "mean_reward": float(mean_reward), "grad_norm": float(grad_norm), "update_ms": t0.elapsed_time(t1),
+               "cuda_graph": not split}
+        if split:
+            out["forward_ms"], out["backward_ms"] = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
         if not math.isfinite(out["loss"]):
             raise RuntimeError("non-finite APG loss (reference train_apg.py:278-287 stops here as well)")
         return out
@@ -198,12 +241,15 @@ def time_apg(batch_size_local: int, horizon: int, iters: int = 3, warmup: int = 
     cfg, env = make_apg_env()
     cfg.horizon, cfg.hidden_size = horizon, hidden_size
     tr = APGTrainer(cfg, env[8], env[9], batch_size_local, output_scale=output_scale)
-    for _ in range(warmup):
-        tr.update()
+    eager = {}
+    for _ in range(max(warmup, 3)):                                   # two eager steps (timed forward / backward split), then the capture
+        o = tr.update()
+        if "forward_ms" in o:
+            eager = {"eager_forward_ms": o["forward_ms"], "eager_backward_ms": o["backward_ms"], "eager_update_ms": o["update_ms"]}
     parallel.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    acc = {"forward_ms": 0.0, "backward_ms": 0.0, "update_ms": 0.0}
+    acc = {"update_ms": 0.0}
     last = {}
     for _ in range(iters):
         last = tr.update()
@@ -212,6 +258,8 @@ def time_apg(batch_size_local: int, horizon: int, iters: int = 3, warmup: int = 
     torch.cuda.synchronize()
     wall = parallel.max_over_ranks((time.perf_counter() - t0) / iters * 1e3, tr.dev)
     res = {k: parallel.max_over_ranks(v / iters, tr.dev) for k, v in acc.items()}
+    res.update(eager)
+    res["cuda_graph"] = bool(last.get("cuda_graph"))
     res.update(wall_update_ms=wall, envs_per_gpu=batch_size_local, horizon=horizon, world=tr.world, solver="CG 4/4 (train_apg.py:101-105)",
                env_steps_per_sec=batch_size_local * tr.world * horizon / (wall * 1e-3), loss=last.get("loss"), grad_norm=last.get("grad_norm"),
                policy_output_scale=output_scale,

@@ -104,7 +104,7 @@ def test_fused_ppo_loss_matches_autograd():
         torch.testing.assert_close(loss, ref, rtol=1e-4, atol=1e-5)
         # a sample whose ratio sits within float32 rounding of a clip boundary may take the other branch (zero vs non-zero gradient)
         edge = ((ratio - 0.8).abs() < 1e-5) | ((ratio - 1.2).abs() < 1e-5)
-        assert int(edge.sum()) <= 4
+        assert int(edge.sum()) <= 1e-3 * n + 2                                    # (an exclusion window, not an error count)
         keep = ~edge.detach()
         torch.testing.assert_close(gm[keep], rm[keep], rtol=1e-3, atol=1e-8)
         if not bool(edge.any()):
