@@ -172,3 +172,45 @@ def test_env_step_vjp_cg_solver_apg_settings(tight_model):
                           P(cot["gr"]), P(g["q"]), P(g["v"]), P(g["aux"]), P(g["act"]), None) == 0
     for k in g:
         assert np.abs(g[k] - g_newton[k]).max() <= 1e-3 * max(1.0, np.abs(g_newton[k]).max()), k
+
+
+@pytest.mark.parametrize("xml,kind", [("humanoid_mjx", "lean"), ("humanoid", "stand")])
+def test_physics_only_vjp_against_finite_differences(xml, kind):
+    """mjxb_step_vjp with in.aux == NULL: the physics step alone (mjx.step; `action` is ctrl, clipped by ctrlrange only), on both
+    humanoid models (humanoid.xml integrates with Euler + eulerdamp, the same implicit-damping solve)."""
+    model = helpers.load(xml, overrides=dict(tolerance=1e-15, iterations=200, ls_iterations=100, ls_tolerance=1e-6))
+    orc = helpers.make_oracle(model)
+    L, blob = helpers.adjoint_host(), modelc.pack_blob(model)
+    nq, nv, nu = model["nq"], model["nv"], model["nu"]
+    rng = np.random.default_rng(7)
+    n = 2
+    q, v, _, _ = helpers.make_states(model, n, 21, kind)
+    ctrl = rng.uniform(-0.9, 0.9, size=(n, nu))
+    ctrl[:, 0] = 1.7                                           # saturated by ctrlrange: zero gradient
+    gq, gv = rng.normal(size=(n, nq)), rng.normal(size=(n, nv))
+
+    def run(q, v, ctrl):
+        out = orc.physics_step(q, v, None, None, ctrl, prec="f64")
+        return out
+
+    def loss(q, v, ctrl):
+        o = run(q, v, ctrl)
+        return (o["qpos"] * gq).sum(1) + (o["qvel"] * gv).sum(1)
+    tape = run(q, v, ctrl)["qacc_warmstart"].copy()
+    g = dict(q=np.zeros((n, nq)), v=np.zeros((n, nv)), act=np.zeros((n, nu)))
+    status = np.zeros(n, dtype=np.int32)
+    assert L.adj_step_vjp(P(blob), None, 1, n, P(q), P(v), None, P(ctrl), P(tape), P(gq), P(gv), None, None, P(g["q"]), P(g["v"]), None,
+                          P(g["act"]), P(status)) == 0
+    assert (status == 0).all()
+    eps = 1e-6
+    base = dict(q=q, v=v, ctrl=ctrl)
+    for name, key, dim in (("v", "v", nv), ("act", "ctrl", nu), ("q", "q", nq)):
+        fd = np.zeros((n, dim))
+        for i in range(dim):
+            a, b = {k: x.copy() for k, x in base.items()}, {k: x.copy() for k, x in base.items()}
+            a[key][:, i] += eps
+            b[key][:, i] -= eps
+            fd[:, i] = (loss(**a) - loss(**b)) / (2 * eps)
+        err = np.abs(fd - g[name]).max(axis=1) / np.maximum(1.0, np.abs(fd).max(axis=1))
+        assert err.max() <= TOL, (xml, name, err)
+    assert np.abs(g["act"][:, 0]).max() == 0.0
