@@ -213,6 +213,24 @@ int mjxb_ppo_loss(int32_t n, int32_t act_dim, const float* mean, const float* lo
 int mjxb_adam(int32_t n, int32_t split, float* param, const float* grad, float* m, float* v, float* step_dev, float lr0, float lr1,
               float b1, float b2, float eps, float grad_scale, void* stream);
 
+/* ---- the learner's collective, fused with the optimiser, over NVLink peer memory (one process per GPU; reference has no multi-GPU code:
+ * SURVEY 8e places the only collective in the gradient all-reduce of train_ppo.py:240-246). Every rank owns a gradient buffer and a
+ * flag block exported through CUDA IPC. mjxb_allreduce_adam is ONE kernel per minibatch: cross-GPU barrier (all backward passes
+ * complete), element-wise sum of ALL ranks' gradients read straight from peer memory in rank order (identical bits on every rank),
+ * division by the world size, Adam on the rank's own parameter copy, cross-GPU barrier (all ranks finished reading). The epoch lives on
+ * the device (CUDA-graph replayable); every spin is bounded and reported through mjxb_comm_error, never a hang.
+ * Set-up: create on every rank, exchange the 128-byte mjxb_comm_local_handles blobs (e.g. torch.distributed.all_gather_object),
+ * connect with all of them in rank order; gradients are accumulated directly in mjxb_comm_grad_buffer. */
+typedef struct mjxb_comm mjxb_comm;
+int mjxb_comm_create(int32_t rank, int32_t world, int32_t n_floats, mjxb_comm** out);
+int mjxb_comm_local_handles(mjxb_comm* c, void* handles_out /* 128 bytes */);
+int mjxb_comm_connect(mjxb_comm* c, const void* all_handles /* world x 128 bytes, rank order */);
+float* mjxb_comm_grad_buffer(mjxb_comm* c);
+int mjxb_comm_error(mjxb_comm* c);
+int mjxb_allreduce_adam(mjxb_comm* c, int32_t n, int32_t split, float* param, float* m, float* v, float* step_dev, float lr0,
+                        float lr1, float b1, float b2, float eps, void* stream);
+void mjxb_comm_destroy(mjxb_comm* c);
+
 /* Generalised advantage estimation over a rollout (reference train_ppo.py:171-202): delta_t = r_t + gamma v_{t+1} (1 - terminated_t) - v_t,
  * adv_t = delta_t + gamma lam (1 - max(terminated_t, truncated_t)) adv_{t+1}, ret_t = adv_t + v_t. reward / terminated / truncated /
  * advantage / ret are [rollout_length, n_env], value is [rollout_length + 1, n_env]; device pointers, one launch. */

@@ -121,17 +121,72 @@ class _FlatAdam:
     """optax.adam / torch.optim.Adam over ONE flat parameter / gradient buffer (include/mjxb.h mjxb_adam): two launches per step, the
     step counter lives on the device (CUDA-graph replayable); [0, split) uses lr0, the rest lr1."""
 
-    def __init__(self, flat_p, flat_g, split: int, lr0: float, lr1: float, eps: float = 1e-8):
+    def __init__(self, flat_p, flat_g, split: int, lr0: float, lr1: float, eps: float = 1e-8, comm=None):
         self.p, self.g, self.split, self.lr0, self.lr1, self.eps = flat_p, flat_g, split, lr0, lr1, eps
         self.m, self.v = torch.zeros_like(flat_p), torch.zeros_like(flat_p)
         self.step_dev = torch.zeros(1, dtype=torch.float32, device=flat_p.device)
+        self.comm = comm                                                   # _PeerComm: gradients of all ranks summed inside the Adam kernel
 
     def step(self, grad_scale: float = 1.0):
         import ctypes as C
         from . import _lib
+        if self.comm is not None:      # one kernel: cross-GPU barrier, sum of every rank's gradients over NVLink peer memory, Adam, barrier
+            _lib.check(_lib.lib().mjxb_allreduce_adam(self.comm.handle, self.p.numel(), self.split, self.p.data_ptr(), self.m.data_ptr(),
+                                                      self.v.data_ptr(), self.step_dev.data_ptr(), self.lr0, self.lr1, 0.9, 0.999, self.eps,
+                                                      C.c_void_p(torch.cuda.current_stream().cuda_stream)), "mjxb_allreduce_adam")
+            return
         _lib.check(_lib.lib().mjxb_adam(self.p.numel(), self.split, self.p.data_ptr(), self.g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
                                         self.step_dev.data_ptr(), self.lr0, self.lr1, 0.9, 0.999, self.eps, float(grad_scale),
                                         C.c_void_p(torch.cuda.current_stream().cuda_stream)), "mjxb_adam")
+
+
+class _PeerComm:
+    """Gradient buffers of all ranks mapped into each other's address space (CUDA IPC over NVLink / NVSwitch, include/mjxb.h mjxb_comm_*):
+    the learner's all-reduce then happens INSIDE the Adam kernel (mjxb_allreduce_adam), not as an NCCL launch."""
+
+    def __init__(self, n_floats: int, device):
+        import ctypes as C
+        from . import _lib
+        L = _lib.lib()
+        self.L, self.n = L, n_floats
+        rank, world = dist.get_rank(), dist.get_world_size()
+        # every step that can fail locally is followed by a collective agreement, so that either all ranks use the communicator or none
+        h, blob, ok = C.c_void_p(), (C.c_char * 128)(), True
+        try:
+            _lib.check(L.mjxb_comm_create(rank, world, n_floats, C.byref(h)), "mjxb_comm_create")
+            _lib.check(L.mjxb_comm_local_handles(h, blob), "mjxb_comm_local_handles")
+        except Exception as e:
+            ok, self._why = False, str(e)
+        self.handle = h if ok else None
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (ok, bytes(blob.raw)))
+        if not all(g[0] for g in gathered):
+            raise RuntimeError("CUDA IPC export failed on a rank")
+        allb = b"".join(g[1] for g in gathered)
+        ok = L.mjxb_comm_connect(h, C.c_char_p(allb)) == 0
+        flags = [None] * world
+        dist.all_gather_object(flags, ok)
+        if not all(flags):
+            raise RuntimeError("CUDA IPC import (peer access) failed on a rank: " + L.mjxb_last_cuda_error().decode())
+        ptr = L.mjxb_comm_grad_buffer(h)
+
+        class _Ext:   # zero-copy torch view of the library-owned (IPC-exported) gradient buffer
+            __cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+        self._ext = _Ext()
+        self.grad = torch.as_tensor(self._ext, device=device)
+        assert self.grad.data_ptr() == int(ptr)
+        dist.barrier()
+
+    def error(self) -> int:
+        return int(self.L.mjxb_comm_error(self.handle))
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.L.mjxb_comm_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
 
 
 @dataclass
@@ -197,7 +252,14 @@ class PPOTrainer:
             allp = self.policy + [self.log_std] + self.value
             n_pol = sum(p.numel() for p in self.policy) + self.log_std.numel()
             self.flat_p = torch.cat([p.detach().reshape(-1) for p in allp]).contiguous()
-            self.flat_g = torch.zeros_like(self.flat_p)
+            self.comm = None
+            if self.world > 1 and os.environ.get("MJXB_PPO_NCCL_ALLREDUCE") is None:
+                try:                                                    # peer-memory gradient exchange fused into the Adam kernel
+                    self.comm = _PeerComm(self.flat_p.numel(), self.dev)
+                except Exception as e:                                  # no CUDA IPC / peer access: NCCL all-reduce inside the update graph
+                    print(f"[ppo] peer-memory communicator unavailable ({type(e).__name__}: {e}); using NCCL")
+                    self.comm = None
+            self.flat_g = self.comm.grad if self.comm is not None else torch.zeros_like(self.flat_p)
             views, o = [], 0
             for p in allp:
                 v = self.flat_p[o:o + p.numel()].view(p.shape).detach().requires_grad_()
@@ -206,7 +268,7 @@ class PPOTrainer:
                 o += p.numel()
             npol = len(self.policy)
             self.policy, self.log_std, self.value = views[:npol], views[npol], views[npol + 1:]
-            self.opt = _FlatAdam(self.flat_p, self.flat_g, n_pol, cfg.lr_policy, cfg.lr_value)
+            self.opt = _FlatAdam(self.flat_p, self.flat_g, n_pol, cfg.lr_policy, cfg.lr_value, comm=self.comm)
             self.opt_p = self.opt_v = None
         else:
             self.opt_p = torch.optim.Adam(self.policy + [self.log_std], lr=cfg.lr_policy, eps=1e-8, capturable=True)
@@ -303,6 +365,8 @@ class PPOTrainer:
         rewards / observations from the step, must stop training instead of being learned from."""
         if self.fused is not None and int(self.fused.error) != 0:
             raise RuntimeError("fused policy kernel reported a tensor-core completion timeout")
+        if getattr(self, "comm", None) is not None and self.comm.error() != 0:
+            raise RuntimeError("a peer did not reach the gradient barrier within the bounded wait (mjxb_allreduce_adam)")
         if not (bool(torch.isfinite(self.r_traj).all()) and bool(torch.isfinite(self.obs).all())):
             raise RuntimeError("non-finite reward / observation in the rollout (MJXB_STATUS_NAN)")
 
@@ -391,8 +455,8 @@ class PPOTrainer:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._minibatch_fb(u["obs"], u["act"], u["logp"], u["ret"], u["adv"], u["idx"], zero=self.fused_learner)
-                if self.world == 1:
-                    self._opt_step()
+                if self.world == 1 or getattr(self, "comm", None) is not None:
+                    self._opt_step()          # sharded + peer communicator: the collective is inside this kernel
                 else:
                     if not self.fused_learner:
                         u["flat"].copy_(torch.cat([p.grad.reshape(-1) for p in params]))
@@ -402,7 +466,8 @@ class PPOTrainer:
             return g
 
         u["st"] = None
-        fused = self.world > 1 and os.environ.get("MJXB_PPO_EAGER_ALLREDUCE") is None
+        peer = getattr(self, "comm", None) is not None
+        fused = self.world > 1 and not peer and os.environ.get("MJXB_PPO_EAGER_ALLREDUCE") is None
         if fused:
             try:
                 u["fb"] = capture(True)
@@ -412,11 +477,12 @@ class PPOTrainer:
                 fused = False
         if not fused:
             u["fb"] = capture(False)
-            if self.world > 1:
+            if self.world > 1 and not peer:
                 u["st"] = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(u["st"], pool=u["fb"].pool()):
                     unflatten_and_step()
-        u["collective_in_graph"] = bool(fused)
+        u["collective_in_graph"] = bool(fused or peer)
+        u["collective"] = "peer-memory sum fused into the Adam kernel" if peer else ("NCCL all-reduce" if self.world > 1 else "none")
         # capture does not execute: run this minibatch now
         u["fb"].replay()
         if u["st"] is not None:
@@ -424,7 +490,7 @@ class PPOTrainer:
             u["st"].replay()
 
     def _allreduce_grads(self, params):
-        if self.world == 1:
+        if self.world == 1 or getattr(self, "comm", None) is not None:      # (peer communicator: summed inside the Adam kernel)
             return
         if self.fused_learner:                 # sum over ranks; _opt_step divides by the world size
             dist.all_reduce(self.flat_g)
@@ -497,7 +563,8 @@ class PPOTrainer:
         out = {"rollout_ms": ev[0].elapsed_time(ev[1]), "update_ms": ev[1].elapsed_time(ev[2]), "iter_ms": ev[0].elapsed_time(ev[2]),
                "train_return_avg": float(self.r_traj.sum(0).mean()), "train_eplen_avg": float(total / max(float(done), 1.0)),
                "minibatches": cfg.epochs * steps_per_epoch, "allreduce_floats": self.n_grads if self.world > 1 else 0,
-               "collective_in_graph": bool(self.upd and self.upd.get("collective_in_graph"))}
+               "collective_in_graph": bool(self.upd and self.upd.get("collective_in_graph")),
+               "collective": (self.upd or {}).get("collective", "none")}
         return out
 
 
@@ -532,6 +599,7 @@ def time_ppo(num_envs_local: int, rollout_length: int, iters: int = 5, warmup: i
     res = {k: parallel.max_over_ranks(v / iters, tr.dev) for k, v in acc.items()}
     res.update(wall_iter_ms=wall, envs_per_gpu=num_envs_local, rollout_length=rollout_length, world=tr.world,
                env_steps_per_sec=num_envs_local * tr.world * rollout_length / (wall * 1e-3), minibatches=last.get("minibatches"),
-               allreduce_floats_per_minibatch=last.get("allreduce_floats"), collective_in_graph=last.get("collective_in_graph"), train_return_avg=last.get("train_return_avg"),
+               allreduce_floats_per_minibatch=last.get("allreduce_floats"), collective_in_graph=last.get("collective_in_graph"),
+               collective=last.get("collective"), train_return_avg=last.get("train_return_avg"),
                cuda_graph=bool(use_cuda_graph), fused_policy_kernel=tr.fused is not None)
     return res

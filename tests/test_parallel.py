@@ -1,8 +1,10 @@
 """N>1 host logic on CPU: world_size-2 gloo process group (env sharding, per-rank keys, max-over-ranks timing)."""
 import os
+import sys
 import socket
 
 import numpy as np
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -51,3 +53,18 @@ def test_shard_range_properties():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+@pytest.mark.gpu
+def test_peer_memory_allreduce_adam_two_gpus():
+    """mjxb_allreduce_adam on 2 GPUs (one process each): the gradient sum over NVLink peer memory fused into the Adam kernel gives the
+    parameters of NCCL all-reduce + torch.optim.Adam, identically on both ranks. Skipped on a box with one GPU."""
+    import subprocess
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "peer_comm_worker.py")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", script], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "peer comm ok" in r.stdout
