@@ -480,17 +480,22 @@ template <bool DBG, int CAP, int MAXCC, int MAXW, bool LS_EXACT, bool SINGLE = f
 __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel* __restrict__ gmodel, const PairParam* __restrict__ pair_param,
                                                             StepArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // programmatic dependent launch: let the successor be staged, then wait for the predecessor's results (no-ops in a plain launch)
+  // programmatic dependent launch (no-ops in a plain launch): let the successor be staged at once; wait for the predecessor's results
+  // only after the work that does not depend on them (staging the model constants) -- except in an overflow tier, whose first read
+  // (its input count) is a result of the predecessor
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  // an overflow tier whose input list is empty (the common case) leaves before it touches shared memory
-  if (A.in_list != nullptr && *reinterpret_cast<volatile int*>(A.in_count) == 0) return;
+  if (A.in_list != nullptr) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // an overflow tier whose input list is empty (the common case) leaves before it touches shared memory
+    if (*reinterpret_cast<volatile int*>(A.in_count) == 0) return;
+  }
   DevModel& C = *reinterpret_cast<DevModel*>(smem_raw);
   {
     const int4* src = reinterpret_cast<const int4*>(gmodel);
     int4* dst = reinterpret_cast<int4*>(smem_raw);
     for (int i = threadIdx.x; i < (int)(sizeof(DevModel) / 16); i += blockDim.x) dst[i] = src[i];
   }
+  if (A.in_list == nullptr) asm volatile("griddepcontrol.wait;" ::: "memory");
   __shared__ int s_reset_count;
   __shared__ int s_spec_done[32];
   if (threadIdx.x == 0) s_reset_count = 0;

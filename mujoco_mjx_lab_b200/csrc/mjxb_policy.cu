@@ -96,7 +96,9 @@ struct PolicyArgs {
 
 __global__ void __launch_bounds__(kThreads, 1) policy_act_kernel(PolicyArgs P) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  mjxb::pdl_prologue();   // staged behind the previous env step's kernels; waits here until their observations are visible
+  // programmatic dependent launch: staged behind the previous env step's kernels. Everything that does not read their results -- TMEM
+  // allocation, barrier init, the first layer's weight image (packed long before) -- runs before the wait, i.e. under their tail
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   unsigned char* sA = smem;
   unsigned char* sW = smem + kABytes;
   float* sBias2 = reinterpret_cast<float*>(smem + kABytes + kWBytes);   // [2][kHid]: layer l+1 is staged while layer l's epilogue reads
@@ -133,6 +135,7 @@ __global__ void __launch_bounds__(kThreads, 1) policy_act_kernel(PolicyArgs P) {
   };
 
   stage_layer(0);
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // from here on the observations of the previous step are read
   // ---- layer-0 A operand: normalised observations, bf16, K padded 54 -> 64 (this thread: features 32*half .. 32*half+31)
   {
 #pragma unroll
