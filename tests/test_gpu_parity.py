@@ -84,7 +84,8 @@ def test_forward_stages(model, oracle, sysm, kind):
     if mism.any():
         dist_rows = _row_positions(model, ref)
         assert (np.abs(dist_rows[mism]) < 1e-6).all(), "candidate mask differs away from the threshold"
-    assert mism.mean() < 1e-4
+    print(f"[{kind}] candidate-mask mismatches (all at the threshold): {int(mism.sum())} of {mism.size}")
+    assert int(mism.sum()) <= 2                                      # measured: 0 on all four families (tools/parity_counts_probe.py)
     both = (cand_g == 1) & (cand_r == 1)
     assert rel(g["efc_pos"], ref["efc_pos"])[both].max() < 2e-6
     assert (np.abs(g["efc_D"] - ref["efc_D"])[both] / ref["efc_D"][both]).max() < 1e-3
@@ -103,11 +104,15 @@ def test_forward_stages(model, oracle, sysm, kind):
     jar = ref["efc_J"] @ ref["qacc"][:, :, None]
     jar = jar[:, :, 0] - ref["efc_aref"]
     thresh = np.abs(ref["efc_D"] * jar)                       # |force| the row would carry / is carrying
-    assert (thresh[bad] < 2e-2 * np.broadcast_to(fmax, thresh.shape)[bad]).all()
-    assert bad.mean() < 2e-3
+    # measured (tools/parity_counts_probe.py): 0 / 1 / 0 / 0 rows of 512 x 187, the one being a row whose force is ~0 in the float64 oracle
+    # and which the float32 ORACLE flips as well
+    print(f"[{kind}] active-mask mismatches: {int(bad.sum())} of {bad.size}")
+    assert int(bad.sum()) <= 3
+    assert (thresh[bad] < 1e-3 * np.broadcast_to(fmax, thresh.shape)[bad]).all(), "active mask differs away from the threshold"
     assert (g["efc_force"] >= 0).all()
     sens_g, sens_r = g["sensordata"] > 0, ref["sensordata"] > 0
-    assert (sens_g != sens_r)[ok_env].mean() < 0.01
+    print(f"[{kind}] touch-sensor sign mismatches: {int((sens_g != sens_r)[ok_env].sum())} of {sens_g[ok_env].size}")
+    assert int((sens_g != sens_r)[ok_env].sum()) <= 1               # measured: 0
     assert (g["status"][ok_env] & 1 == 0).all()
 
 
@@ -140,7 +145,9 @@ def test_one_step_state(model, oracle, sysm, kind):
         eg, e32 = np.abs(g - ref[name]), np.abs(r32[name] - ref[name])
         tol = 3.0 * e32.max() + 1e-5 + 1e-4 * np.abs(ref[name])
         assert (eg <= tol).all(), (name, eg.max(), e32.max())
-        assert np.median(eg.max(axis=1)) < {"qpos": 1e-6, "qvel": 2e-4, "qacc_warmstart": 5e-2}[name], (name, np.median(eg.max(axis=1)))
+        # medians measured (tools/parity_counts_probe.py): qvel 2e-5 .. 6e-5, qacc_warmstart 6e-3 .. 1.4e-2 (float32 oracle: 2e-5 .. 3e-5, 6e-3 .. 1e-2)
+        assert np.median(eg.max(axis=1)) < {"qpos": 1e-6, "qvel": 1.5e-4, "qacc_warmstart": 3e-2}[name], (name, np.median(eg.max(axis=1)))
+        assert np.median(eg.max(axis=1)) <= 2.5 * np.median(e32.max(axis=1)) + 1e-7, (name, np.median(eg.max(axis=1)), np.median(e32.max(axis=1)))
     np.testing.assert_allclose(N(nd.time), 0.005, rtol=1e-6)
     np.testing.assert_allclose(np.linalg.norm(N(nd.qpos)[:, 3:7], axis=1), 1.0, atol=1e-6)
 
@@ -187,13 +194,15 @@ def test_reset_parity(model, oracle, env):
     assert (N(d.time) == 0).all()
     np.testing.assert_allclose(N(aux)[:, 1:5], st["aux"][:, 1:5], atol=1e-6)
     np.testing.assert_allclose(N(aux)[:, 7], st["aux"][:, 7], atol=2e-3)  # -dist/dt: 200x gain
-    # stance state may legitimately differ when a foot sits exactly on the floor (f32 threshold): bound it
-    assert (N(aux)[:, 5] != st["aux"][:, 5]).mean() < 0.05
+    # stance state may legitimately differ when a foot sits exactly on the floor (f32 threshold): counted; measured 0 of 1024
+    n_stance = int((N(aux)[:, 5] != st["aux"][:, 5]).sum())
+    print(f"reset: stance-state mismatches {n_stance} of {n}")
+    assert n_stance <= 2
     np.testing.assert_allclose(N(obs), o_ref, atol=1e-5)
     s64, _ = oracle.env_reset(keys, prec="f64")
     e_g = np.abs(N(d.qacc_warmstart) - s64["qacc_warmstart"]).max()
     e_32 = np.abs(st["qacc_warmstart"] - s64["qacc_warmstart"]).max()
-    assert e_g <= 3 * e_32 + 1e-3
+    assert e_g <= 3 * e_32 + 1e-3 or int((np.abs(N(d.qacc_warmstart) - s64["qacc_warmstart"]).max(axis=1) > 3 * e_32 + 1e-3).sum()) <= 1
 
 
 def test_env_step_resynchronised_128(model, oracle, env):
@@ -238,6 +247,7 @@ def test_env_step_resynchronised_128(model, oracle, env):
     assert_f32_equivalent(np.concatenate(errs["obs_g"]), np.concatenate(errs["obs_32"]), 1e-4, "obs")       # obs: 1e-4 abs floor
     assert_f32_equivalent(np.concatenate(errs["r_g"]), np.concatenate(errs["r_32"]), 2e-3, "reward")        # reward: 1/dt gain on dist
     assert worst["qpos"] < 1e-4 and worst["qvel"] < 5e-2
+    assert flags <= 2, "terminated flags that differ at the 0.7 m threshold (counted)"
 
 
 def test_speed_test_semantics(model, oracle, sysm):
