@@ -119,6 +119,8 @@ int mjxb_model_create(const void* blob, size_t blob_bytes, const mjxb_env_config
 #define MJXB_FLAG_DENSE_CHOL 2u    /* dense right-looking Cholesky instead of the generated tree-ordered elimination */
 #define MJXB_FLAG_INLINE_RESET 4u  /* auto-reset runs inline instead of in deferred packed rounds */
 #define MJXB_FLAG_NO_SPEC_RESET 8u /* never run the auto-reset speculatively beside the step (the small-batch latency path, <= 1184 envs) */
+#define MJXB_FLAG_NO_WORK_SORT 16u /* never deal the envs of a large batch (>= 16,384) to the CTAs in order of their previous step's Newton
+                                      iteration count (the work-sorted schedule: one extra small launch per step, identical results) */
 #define MJXB_FLAG_BUILD_EXACT 256u /* (reported only) the library is the reference-arithmetic build: no fast-math, no FMA contraction */
 int mjxb_model_create_ex(const void* blob, size_t blob_bytes, const mjxb_env_config* cfg, int device, uint32_t flags,
                          mjxb_model** out);

@@ -65,6 +65,8 @@ struct Tuning {
   bool inline_reset = false, sync_tiers = false, spec_reset = true;
   bool host_direct = true, direct_obs = true, direct_scalars = true;
   int host_chunks = 0;
+  int sort_min_env = 16384;  // work-sorted scheduling from this batch size on (0 = never); MJXB_SORT_MIN_ENV
+  int sort_seg_shift = 15;   // segment = 2^shift envs (one sort CTA each); the host pipeline uses its input-chunk size instead
 };
 
 // Per-stream launch scratch (overflow counters + lists + per-CTA reset queues). One entry per stream that has launched on the model, so
@@ -72,7 +74,8 @@ struct Tuning {
 // new buffer, the old one is retired until mjxb_model_destroy), so CUDA graphs captured earlier stay valid.
 struct Scratch {
   cudaStream_t stream = nullptr;
-  int* buf = nullptr;   // [0] countA, [1] doneA, [2] countB, [3] doneB, [4..4+cap) listA (main -> mid), [4+cap..) listB (mid -> big), then reset queues
+  int* buf = nullptr;   // [0] countA, [1] doneA, [2] countB, [3] doneB, [4..4+cap) listA (main -> mid), [4+cap..) listB (mid -> big), then reset queues,
+                        // then the work-sorted schedule: perm [cap] ints and the cost keys [cap] bytes
   int cap = 0;
 };
 
@@ -87,7 +90,8 @@ struct mjxb_model {
   mutable std::vector<Scratch> scratch;      // live entries, one per stream
   mutable std::vector<int*> scratch_retired; // superseded buffers (freed at destroy)
   Arena arena;
-  size_t scratch_ints(int n_env) const { return 3 * (size_t)n_env + 4 + (size_t)num_sms * kMaxWarps * 2; }
+  size_t sched_offset(int n_env) const { return 3 * (size_t)n_env + 4 + (size_t)num_sms * kMaxWarps * 2; }   // ints before perm
+  size_t scratch_ints(int n_env) const { return sched_offset(n_env) + (size_t)n_env + ((size_t)n_env + 3) / 4; }
 };
 
 namespace {
@@ -136,6 +140,7 @@ int arena_ensure(mjxb_model* m, int n) {
     CU(cudaStreamCreateWithFlags(&a.pipe[i], cudaStreamNonBlocking));
     CU(cudaMalloc(&a.pipe_ovf[i], m->scratch_ints(a.chunk) * sizeof(int)));
     CU(cudaMemsetAsync(a.pipe_ovf[i], 0, 4 * sizeof(int), a.stream));
+    CU(cudaMemsetAsync(a.pipe_ovf[i] + m->sched_offset(a.chunk) + a.chunk, 0, (size_t)a.chunk, a.stream));
   }
   CU(cudaMalloc(&a.ready, Arena::kReadyMax * sizeof(unsigned)));
   CU(cudaMemsetAsync(a.ready, 0, Arena::kReadyMax * sizeof(unsigned), a.stream));
@@ -167,6 +172,7 @@ int scratch_for(const mjxb_model* m, cudaStream_t stream, int n_env, int** buf, 
   int* nb = nullptr;
   CU(cudaMalloc(&nb, m->scratch_ints(n_env) * sizeof(int)));
   CU(cudaMemsetAsync(nb, 0, 4 * sizeof(int), stream));
+  CU(cudaMemsetAsync(nb + m->sched_offset(n_env) + n_env, 0, (size_t)n_env, stream));   // cost keys: no hint yet
   if (s == nullptr) { m->scratch.push_back(Scratch()); s = &m->scratch.back(); s->stream = stream; }
   else m->scratch_retired.push_back(s->buf);  // earlier launches / captured graphs may still reference it
   s->buf = nb; s->cap = n_env;
@@ -209,6 +215,17 @@ int launch(const mjxb_model* m, const StepArgs& args_in, bool dbg, cudaStream_t 
     grid = (args.n_env + per_sm - 1) / per_sm;
     if (grid > m->num_sms) grid = m->num_sms;
   }
+  // work-sorted scheduling: the envs of every segment are dealt to the CTAs by descending cost key of their previous step
+  args.perm = nullptr; args.work_out = nullptr;
+  int extra_launches = 0;
+  if (m->tune.sort_min_env > 0 && args.n_env >= m->tune.sort_min_env && (args.mode == MODE_ENV_STEP || args.mode == MODE_PHYS_STEP) && !dbg) {
+    int* perm = ovf + m->sched_offset(cap);
+    uint8_t* work = reinterpret_cast<uint8_t*>(perm + cap);
+    const int shift = args.in_ready != nullptr ? args.in_ready_shift : m->tune.sort_seg_shift;  // streamed inputs: never reorder across chunks
+    launch_pdl(mjxb_sort_work_kernel, dim3((args.n_env + (1 << shift) - 1) >> shift), dim3(1024), 0, stream, (const uint8_t*)work, perm, args.n_env, shift);
+    args.perm = perm; args.work_out = work;
+    extra_launches = 1;
+  }
   const size_t smem_main = m->smem - (size_t)(m->warps - warps) * sizeof(WarpS<CAP_MAIN, MAXCC_MAIN>);
   args.reset_stride = ((args.n_env + grid * warps - 1) / (grid * warps)) * warps;
   const bool ls = m->host.ls_exact != 0 && m->host.solver == 2;  // fast instantiation: Newton + exact line search; else the general one
@@ -224,11 +241,12 @@ int launch(const mjxb_model* m, const StepArgs& args_in, bool dbg, cudaStream_t 
   if (single) launch_pdl(mjxb_step_kernel<false, CAP_MAIN, MAXCC_MAIN, WARPS_MAIN, true, true>, dim3(grid), dim3(warps * 32), smem_main, stream,
                          (const DevModel*)m->dev, (const PairParam*)m->dev_pp, args);
   else MJXB_LAUNCH(CAP_MAIN, MAXCC_MAIN, WARPS_MAIN, grid, warps * 32, smem_main);
-  g_mjxb_launches += 3;   // main tier + the two overflow tiers below (each leaves at once when its list is empty)
+  g_mjxb_launches += 3 + extra_launches;   // (the schedule sort) + main tier + the two overflow tiers below (each leaves at once when its list is empty)
   cudaError_t e = cudaGetLastError();
   const bool sync_tiers = m->tune.sync_tiers;  // debugging aid: attribute a device fault to its tier
   if (sync_tiers && e == cudaSuccess) { e = cudaStreamSynchronize(stream); if (e != cudaSuccess) fprintf(stderr, "[mjxb] main tier failed: %s\n", cudaGetErrorString(e)); }
   args.in_ready = nullptr;  // only the first pass waits for streamed inputs
+  args.perm = nullptr;      // (the overflow tiers read their own lists; they still leave cost keys)
   if (e == cudaSuccess) {  // mid tier (64 rows / 24 contacts) over the envs the main tile could not hold; usually few: exits at once when empty
     args.in_count = ovf; args.in_done = ovf + 1; args.in_list = listA; args.out_count = ovf + 2; args.out_list = listB;
     const int wm = m->warps_mid;
@@ -338,6 +356,8 @@ int mjxb_model_create_ex(const void* blob, size_t blob_bytes, const mjxb_env_con
   m->tune.sync_tiers = getenv("MJXB_SYNC_TIERS") != nullptr;
   m->tune.spec_reset = env_int("MJXB_SPEC_RESET", 1) != 0 && !m->tune.inline_reset && !(flags & MJXB_FLAG_NO_SPEC_RESET);
   m->tune.host_chunks = env_int("MJXB_HOST_CHUNKS", 0);
+  m->tune.sort_min_env = (flags & MJXB_FLAG_NO_WORK_SORT) ? 0 : env_int("MJXB_SORT_MIN_ENV", m->tune.sort_min_env);
+  m->tune.sort_seg_shift = env_int("MJXB_SORT_SEG_SHIFT", m->tune.sort_seg_shift);
   m->tune.host_direct = env_int("MJXB_HOST_DIRECT", 1) != 0;
   m->tune.direct_obs = env_int("MJXB_DIRECT_OBS", 1) != 0;
   m->tune.direct_scalars = env_int("MJXB_DIRECT_SCALARS", 1) != 0;
@@ -427,6 +447,7 @@ int mjxb_model_flags(const mjxb_model* m) {
   if (!m->host.tree_chol_ok) f |= MJXB_FLAG_DENSE_CHOL;
   if (m->tune.inline_reset) f |= MJXB_FLAG_INLINE_RESET;
   if (!m->tune.spec_reset) f |= MJXB_FLAG_NO_SPEC_RESET;
+  if (m->tune.sort_min_env <= 0) f |= MJXB_FLAG_NO_WORK_SORT;
 #if MJXB_EXACT
   f |= MJXB_FLAG_BUILD_EXACT;
 #endif

@@ -44,6 +44,10 @@ struct StepArgs {
   // re-initialises it from its key at the same time (single_reset depends on the key alone), and the partner's result is stored only
   // if the step finished the episode -- the reset no longer runs as a second, serialised pass of the pipeline
   int spec_reset;
+  // work-sorted scheduling (large batches): `perm` lists the envs of each segment by descending predicted cost, so that the 16 envs a CTA
+  // runs in lockstep need about the same number of Newton iterations; every env leaves its cost key (this step's iteration count) in
+  // `work_out` for the next launch on the stream. A stale or missing hint only costs time: results do not depend on the order.
+  const int* perm; uint8_t* work_out;
   int lockstep;          // CTA barriers keep the warps of an SM in the same code region (instruction-cache locality)
   int lockstep_group;    // warps per barrier group (0 = the whole CTA)
   // host-buffer pipeline: action / keys arrive in chunks of (1 << in_ready_shift) envs while the kernel already runs; the copy
@@ -456,6 +460,9 @@ __device__ int g_stage_clock[4096 * 32];
 #else
 #define MJXB_STAMP(i) do { } while (0)
 #endif
+#ifndef MJXB_WORK_KEY_ITER
+#define MJXB_WORK_KEY_ITER 4   // cost key of the work-sorted scheduling: iterations * this + (candidate rows / 8, clipped)
+#endif
 #ifndef MJXB_FACTOR_REUSE
 #define MJXB_FACTOR_REUSE 1
 #endif
@@ -469,6 +476,48 @@ __device__ __forceinline__ void group_sync(int warp, int g) {
   const int grp = warp / g;
   const int cnt = min(g, nwarp - grp * g) * 32;
   asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(cnt) : "memory");
+}
+
+// Segmented counting sort of the envs by descending cost key (one CTA per segment of 2^seg_shift envs, 256 bins): perm[lo .. hi) = the envs
+// of the segment, heaviest first. The order inside a bin is arbitrary (atomics) -- nothing downstream depends on it.
+__global__ void __launch_bounds__(1024) mjxb_sort_work_kernel(const uint8_t* __restrict__ work, int* __restrict__ perm, int n, int seg_shift) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  __shared__ int hist[256];
+  __shared__ int base[256];
+  const int lo = blockIdx.x << seg_shift, hi = min(n, lo + (1 << seg_shift)), lane = threadIdx.x & 31;
+  if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+  __syncthreads();
+  for (int i0 = lo + (threadIdx.x & ~31); i0 < hi; i0 += blockDim.x) {   // warp-uniform trip count: match_any needs the whole warp
+    const int i = i0 + lane;
+    const int key = i < hi ? work[i] : 256 + lane;                       // out-of-range lanes get distinct dummy keys
+    const unsigned peers = __match_any_sync(FULL, key);
+    if (i < hi && lane == __ffs(peers) - 1) atomicAdd(&hist[key], __popc(peers));
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {   // exclusive prefix over the bins in descending key order
+    int run = 0;
+    for (int b0 = 0; b0 < 256; b0 += 32) {
+      const int bin = 255 - (b0 + lane);
+      const int c = hist[bin];
+      int inc = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
+      base[bin] = run + inc - c;
+      run += __shfl_sync(FULL, inc, 31);
+    }
+  }
+  __syncthreads();
+  for (int i0 = lo + (threadIdx.x & ~31); i0 < hi; i0 += blockDim.x) {
+    const int i = i0 + lane;
+    const int key = i < hi ? work[i] : 256 + lane;
+    const unsigned peers = __match_any_sync(FULL, key);
+    const int leader = __ffs(peers) - 1;
+    int pos = 0;
+    if (i < hi && lane == leader) pos = atomicAdd(&base[key], __popc(peers));
+    pos = __shfl_sync(FULL, pos, leader) + __popc(peers & ((1u << lane) - 1u));
+    if (i < hi) perm[lo + pos] = i;
+  }
 }
 
 // lane-per-row loop over the candidate rows with a compile-time trip bound (NSTRIP = ceil(CAP / 32), 1 for the main tier): a plain
@@ -536,7 +585,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
     if (!reset_phase) {
       const int item = (round * gridDim.x + blockIdx.x) * nslot + wslot;
       valid = item < n_items;
-      env = valid ? (consuming ? A.in_list[item] : item) : (consuming ? A.in_list[0] : 0);
+      env = valid ? (consuming ? A.in_list[item] : (A.perm != nullptr ? A.perm[item] : item)) : (consuming ? A.in_list[0] : 0);
     } else {
       const int idx = (round - n_rounds) * nwarp + warp;
       valid = idx < n_reset;
@@ -1547,6 +1596,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
 
       if (A.lockstep == 3 && pass == 0) { while (__syncthreads_or(0)) {} }  // finished warps keep answering the per-round barrier
       else if (A.lockstep > 0 && A.lockstep != 2 && pass == 0) group_sync(warp, A.lockstep_group);  // ... and leave it together (early finishers would idle at the round barrier anyway)
+      if (A.work_out != nullptr && valid && !spec_partner && lane == 0) A.work_out[env] = (uint8_t)min(niter * MJXB_WORK_KEY_ITER + min(nrow >> 3, MJXB_WORK_KEY_ITER - 1), 255);
       if (DBG) {
         if (lane < NV) {
           if (A.dbg.qacc) A.dbg.qacc[(size_t)env * NV + lane] = qacc;

@@ -80,3 +80,35 @@ def test_speculative_reset_is_bit_identical(model):
             assert torch.equal(sa[0].qpos, sb[0].qpos) and torch.equal(sa[0].qvel, sb[0].qvel) and torch.equal(sa[1], sb[1]), (n, t)
             assert torch.equal(sa[0].qacc_warmstart, sb[0].qacc_warmstart) and torch.equal(sa[0].time, sb[0].time), (n, t)
         assert resets >= max(1, n // 7)
+
+
+def test_work_sorted_schedule_is_bit_identical(model):
+    """Large batches deal the envs to the CTAs by descending Newton-iteration count of their previous step (mjxb_abi.cu launch(),
+    mjxb_sort_work_kernel): the order in which envs are processed changes, no result does -- device API over steps that reset envs
+    (a batch size that is not a multiple of the sort segment), and the pinned host pipeline whose input chunks are the sort segments."""
+    import helpers
+    from mujoco_mjx_lab_b200 import _lib, training_utils
+    env_a = training_utils.load_model_and_create_env("", helpers.env_config(), model=model)
+    env_b = training_utils.load_model_and_create_env("", helpers.env_config(), model=model, flags=_lib.FLAG_NO_WORK_SORT)
+    assert env_b[9].sys.lib.mjxb_model_flags(env_b[9].sys.handle) & _lib.FLAG_NO_WORK_SORT
+    assert env_a[9].sys.lib.mjxb_model_flags(env_a[9].sys.handle) & _lib.FLAG_NO_WORK_SORT == 0
+    n = 40000 + 123
+    keys = helpers.ppo_keys(5, n)
+    sa, oa = env_a[8](keys)
+    sb, ob = env_b[8](keys)
+    sa[1][::7, 8] = 999.0                                    # force truncations -> resets in the very first step
+    sb[1][::7, 8] = 999.0
+    launches0 = env_a[9].sys.lib.mjxb_launch_count()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    resets = 0
+    for t in range(24):
+        act = torch.randn(n, 21, device="cuda", generator=g) * (3.0 if t % 3 == 0 else 1.0)
+        rk = helpers.ppo_keys(200 + t, n)
+        sa, oa, ra, tea, tra = env_a[9].autoreset(sa, act, rk)
+        sb, ob, rb, teb, trb = env_b[9].autoreset(sb, act, rk)
+        resets += int(torch.maximum(tea, tra).sum())
+        assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(tea, teb) and torch.equal(tra, trb), t
+        assert torch.equal(sa[0].qpos, sb[0].qpos) and torch.equal(sa[0].qvel, sb[0].qvel) and torch.equal(sa[1], sb[1]), t
+        assert torch.equal(sa[0].qacc_warmstart, sb[0].qacc_warmstart) and torch.equal(sa[0].time, sb[0].time), t
+    assert resets > 0
+    assert env_a[9].sys.lib.mjxb_launch_count() - launches0 == 24 * (4 + 3)      # sorted: 4 launches per step; plain: 3
