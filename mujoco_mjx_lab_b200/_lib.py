@@ -42,7 +42,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for target in (LIB_PATH, EXACT_LIB_PATH):
         stale = force or not os.path.exists(target) or any(os.path.getmtime(s) > os.path.getmtime(target) for s in srcs)
         if stale:
-            r = subprocess.run(["make", "-C", csrc, "-B", "../" + os.path.basename(target)], capture_output=True, text=True)
+            r = subprocess.run(["make", "-C", csrc, "-j8"] + (["-B"] if force else []) + ["../" + os.path.basename(target)], capture_output=True, text=True)
             if verbose or r.returncode != 0:
                 print(r.stdout[-4000:], r.stderr[-4000:])
             if r.returncode != 0:

@@ -461,7 +461,12 @@ __device__ int g_stage_clock[4096 * 32];
 #define MJXB_STAMP(i) do { } while (0)
 #endif
 #ifndef MJXB_WORK_KEY_ITER
-#define MJXB_WORK_KEY_ITER 4   // cost key of the work-sorted scheduling: iterations * this + (candidate rows / 8, clipped)
+// cost key of the work-sorted schedule = this step's Newton iterations * ITER + candidate rows * ROW. The candidate-row count of the
+// previous step predicts the next step's iteration count better than the previous iteration count does (tools/niter_predict_dump.py on the
+// trajectory distribution: mean over groups of 16 of the largest count 5.86 unsorted, 5.57 by iterations, 5.40 by rows or by this key,
+// 5.2 for a boosted-tree regressor on every previous-step feature, 3.04 with hindsight), and it also sorts by the cost of an iteration.
+#define MJXB_WORK_KEY_ITER 4
+#define MJXB_WORK_KEY_ROW 2
 #endif
 #ifndef MJXB_FACTOR_REUSE
 #define MJXB_FACTOR_REUSE 1
@@ -1596,7 +1601,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
 
       if (A.lockstep == 3 && pass == 0) { while (__syncthreads_or(0)) {} }  // finished warps keep answering the per-round barrier
       else if (A.lockstep > 0 && A.lockstep != 2 && pass == 0) group_sync(warp, A.lockstep_group);  // ... and leave it together (early finishers would idle at the round barrier anyway)
-      if (A.work_out != nullptr && valid && !spec_partner && lane == 0) A.work_out[env] = (uint8_t)min(niter * MJXB_WORK_KEY_ITER + min(nrow >> 3, MJXB_WORK_KEY_ITER - 1), 255);
+      if (A.work_out != nullptr && valid && !spec_partner && lane == 0) A.work_out[env] = (uint8_t)min(niter * MJXB_WORK_KEY_ITER + nrow * MJXB_WORK_KEY_ROW, 255);
       if (DBG) {
         if (lane < NV) {
           if (A.dbg.qacc) A.dbg.qacc[(size_t)env * NV + lane] = qacc;

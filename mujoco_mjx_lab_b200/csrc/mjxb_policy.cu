@@ -1,15 +1,21 @@
 // mjxb_policy.cu -- fused policy inference for the rollout loop (reference train_ppo.py:135-140,
 // src/networks.py:55-61,105-112): obs normalisation -> 54-256-256-256-21 tanh MLP -> Gaussian sample -> log-prob, ONE launch.
 //
-// sm_100a design: a CTA owns a tile of 128 envs. The four GEMMs run on the 5th-generation tensor cores (tcgen05.mma, kind::f16 with
-// bf16 operands, fp32 accumulation in TMEM); activations never leave the SM: the epilogue reads the accumulator from TMEM
-// (tcgen05.ld), applies bias + tanh, and writes the bf16 activations straight into the canonical K-major shared-memory layout that
-// the next layer's A descriptor reads. Weights are pre-packed (mjxb_policy_pack_weight) into the canonical K-major core-matrix
-// layout, so loading a layer is a linear 16-byte-vector copy of <= 128 KB out of L2 (no TMA descriptors needed for a 0.3 MB model).
+// sm_100a design (round 2: persistent, warp-specialised, two env tiles in flight per SM):
+//   * one CTA per SM, 10 warps: warp 0 = weight producer, warp 1 = MMA issuer, warps 2-5 / 6-9 = the epilogue groups of tile slot 0 / 1;
+//   * a tile is 128 envs (MMA M); each slot owns a 64 KB activation buffer in the canonical K-major layout and 256 TMEM columns;
+//   * the four GEMMs of a tile run on the 5th-generation tensor cores (tcgen05.mma kind::f16, bf16 operands, fp32 accumulators in TMEM),
+//     issued by ONE thread; the two slots are a layer apart, so the MMAs of one tile run while the other tile's epilogue group reads its
+//     accumulator (tcgen05.ld), adds the bias, applies tanh and writes the next layer's A operand -- activations never leave the SM;
+//   * weights are pre-packed (mjxb_policy_pack_weight) into 16 KB chunks, each a ready-to-use canonical K-major B operand
+//     (hidden layers: 32 of K x 256 of N; output layer: 256 x 32), and stream through a 4-stage shared-memory ring with one bulk-copy
+//     (cp.async.bulk -> mbarrier complete_tx) per chunk: the producer thread runs ahead of the MMAs by up to 64 KB;
+//   * a tile's observations, noise and actions are contiguous blocks of global memory: each moves as ONE bulk copy through staging;
+//   * pipelines are mbarriers only (ring full / empty, accumulator full, A-operand ready); no CTA-wide barrier after the prologue.
 //
-// Shared-memory operand layout (no swizzle; core matrix = 8 rows x 16 bytes, stored contiguously):
-//   A (activations, 128 rows x K):  byte(r,k) = (r%8)*16 + (r/8)*128 + (k/8)*2048 + (k%8)*2      -> SBO = 128, LBO = 2048
-//   B (weights W^T, N rows x K):     byte(n,k) = (n%8)*16 + (n/8)*(K/8)*128 + (k/8)*128 + (k%8)*2 -> SBO = 16*K, LBO = 128
+// Shared-memory operand layouts (no swizzle; core matrix = 8 rows x 16 bytes, stored contiguously):
+//   A (activations, 128 rows x K):   byte(r,k) = (r%8)*16 + (r/8)*128 + (k/8)*2048 + (k%8)*2         -> SBO = 128, LBO = 2048
+//   B chunk (W^T, N rows x Kc of K):  byte(n,k) = (n%8)*16 + (n/8)*(Kc/8)*128 + (k/8)*128 + (k%8)*2   -> SBO = 16*Kc, LBO = 128
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <atomic>
@@ -22,15 +28,31 @@
 
 namespace mjxbp {
 
-constexpr int kTile = 128;      // envs per CTA = MMA M
+constexpr int kTile = 128;      // envs per tile = MMA M
 constexpr int kHid = 256;       // hidden width = MMA N of the hidden layers
 constexpr int kInPad = 64;      // obs_dim 54 padded to a multiple of 16
 constexpr int kOutPad = 32;     // action dim 21 padded to a multiple of 16
-constexpr int kThreads = 256;
-constexpr int kABytes = kTile * kHid * 2;        // 64 KB
-constexpr int kWBytes = kHid * kHid * 2;         // 128 KB (largest layer)
-constexpr int kSmemBytes = kABytes + kWBytes + 2 * kHid * 4 + 64;   // + double-buffered bias + mbarrier + TMEM slot
-constexpr uint32_t kTmemCols = 256;
+constexpr int kSlots = 2;       // env tiles in flight per CTA
+constexpr int kEpiWarps = 4;    // per slot: one warp per TMEM lane quadrant
+constexpr int kThreads = 32 * (2 + kSlots * kEpiWarps);   // producer + MMA issuer + 2 x 4 epilogue warps = 320
+constexpr int kABytes = kTile * kHid * 2;                 // 64 KB per slot
+constexpr int kChunkBytes = 16384;                        // one weight chunk = one ring stage
+constexpr int kStages = 4;
+constexpr int kBiasFloats = 3 * kHid + kOutPad;
+constexpr int kOffRing = kSlots * kABytes;
+constexpr int kOffBias = kOffRing + kStages * kChunkBytes;
+constexpr int kOffNorm = kOffBias + kBiasFloats * 4;      // observation statistics: mean[64], 1 / sqrt(var + 1e-8)[64]
+constexpr int kOffLogStd = kOffNorm + 2 * kInPad * 4;     // log_std[32], exp(log_std)[32], exp(-2 log_std)[32]
+constexpr int kEpsCols = 24;                              // noise staging of one slot holds 128 x act_dim floats for act_dim <= 24
+constexpr int kEpsBytes = kTile * kEpsCols * 4;           // (wider action vectors read their noise thread-per-row)
+constexpr int kOffEps = kOffLogStd + 3 * kOutPad * 4;
+constexpr int kOffBar = kOffEps + kSlots * kEpsBytes;
+constexpr int kNumBar = 2 * kStages + 4 * kSlots;         // ring full / empty, accumulator full, A ready, observations / noise landed
+constexpr int kOffMisc = kOffBar + kNumBar * 8;           // TMEM base slot, abort flag
+constexpr int kSmemBytes = kOffMisc + 16;
+constexpr uint32_t kTmemCols = 512;                       // 256 fp32 accumulator columns per slot
+static_assert(kSmemBytes <= 232448, "exceeds the 227 KB opt-in shared memory of sm_100");
+static_assert(kHid * 32 * 2 == kChunkBytes && kOutPad * kHid * 2 == kChunkBytes, "chunk geometry");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -58,6 +80,9 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {   // arrives on `bar` when every MMA issued so far by this thread has retired
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+}
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -79,6 +104,49 @@ __device__ __forceinline__ float tanh_fast(float x) {
   return y;
 }
 
+// bounded mbarrier wait: a completion that never comes (a fault, a lost copy) sets the abort flag, every role leaves its loop, and the
+// launch reports through *error instead of hanging the device
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatile int* abort_flag, int* error) {
+  for (int spin = 0; spin < (1 << 22); spin++) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return true;
+    if ((spin & 255) == 255 && *abort_flag) return false;
+  }
+  *abort_flag = 1;
+  if (error) *error = 1;
+  return false;
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+
+#ifndef MJXB_POLICY_TRACE
+#define MJXB_POLICY_TRACE 0
+#endif
+#if MJXB_POLICY_TRACE
+__device__ unsigned long long g_trace[4096];
+// CTA 0 only; three writer threads (MMA issuer = region 0, thread 0 of the epilogue group of slot s = region 1 + s), each with its own
+// cursor (a register): one clock64 read and one fire-and-forget store per stamp
+#define TRACE_DECL int trace_n = 0
+__device__ __forceinline__ void trace(int region, int& n, int slot, unsigned long long tag) {
+  if (blockIdx.x != 0 || n >= 640) return;
+  g_trace[region * 1280 + 2 * n] = tag | ((unsigned long long)slot << 32);
+  g_trace[region * 1280 + 2 * n + 1] = (unsigned long long)clock64();
+  n++;
+}
+#define TRACE(slot, tag) trace(trace_region, trace_n, slot, tag)
+#else
+#define TRACE_DECL
+#define TRACE(slot, tag)
+#endif
+
 struct PolicyArgs {
   int n_env, obs_dim, act_dim;
   const float* obs;        // [n, obs_dim]
@@ -91,179 +159,334 @@ struct PolicyArgs {
   float* act;              // [n, act_dim]
   float* logp;             // [n]
   float* mean;             // [n, act_dim] or NULL
-  int* error;              // device flag: set to 1 if an MMA completion was not observed within the bounded wait
+  int* error;              // device flag: set to 1 if a pipeline completion was not observed within the bounded wait
 };
+
+// weight chunks of layer l: count, K extent of a chunk, N
+__device__ __forceinline__ int layer_chunks(int l) { return l == 0 ? kInPad / 32 : (l == 3 ? 1 : kHid / 32); }
+__device__ __forceinline__ int layer_kc(int l) { return l == 3 ? kHid : 32; }
+__device__ __forceinline__ int layer_n(int l) { return l == 3 ? kOutPad : kHid; }
 
 __global__ void __launch_bounds__(kThreads, 1) policy_act_kernel(PolicyArgs P) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  // programmatic dependent launch: staged behind the previous env step's kernels. Everything that does not read their results -- TMEM
-  // allocation, barrier init, the first layer's weight image (packed long before) -- runs before the wait, i.e. under their tail
+  // programmatic dependent launch: staged behind the previous env step's kernels; TMEM allocation and barrier init run under their tail
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  unsigned char* sA = smem;
-  unsigned char* sW = smem + kABytes;
-  float* sBias2 = reinterpret_cast<float*>(smem + kABytes + kWBytes);   // [2][kHid]: layer l+1 is staged while layer l's epilogue reads
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + kABytes + kWBytes + 2 * kHid * 4);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kABytes + kWBytes + 2 * kHid * 4 + 16);
+  float* sBias = reinterpret_cast<float*>(smem + kOffBias);
+  float* sNorm = reinterpret_cast<float*>(smem + kOffNorm);
+  float* sLogStd = reinterpret_cast<float*>(smem + kOffLogStd);
+  const uint32_t bar0 = smem_u32(smem + kOffBar);
+  auto bar_wfull = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  auto bar_wempty = [&](int i) { return bar0 + 8u * (uint32_t)(kStages + i); };
+  auto bar_accfull = [&](int s) { return bar0 + 8u * (uint32_t)(2 * kStages + s); };
+  auto bar_aready = [&](int s) { return bar0 + 8u * (uint32_t)(2 * kStages + kSlots + s); };
+  auto bar_obsfull = [&](int s) { return bar0 + 8u * (uint32_t)(2 * kStages + 2 * kSlots + s); };
+  auto bar_epsfull = [&](int s) { return bar0 + 8u * (uint32_t)(2 * kStages + 3 * kSlots + s); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffMisc);
+  volatile int* abort_flag = reinterpret_cast<volatile int*>(smem + kOffMisc + 4);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int row = 32 * (warp & 3) + lane;   // TMEM lane == env row of the tile (a warp may only touch lanes 32*(warp%4)..+31)
-  const int half = warp >> 2;               // which half of the columns this thread handles
-  const int env = blockIdx.x * kTile + row;
-  const bool live = env < P.n_env;
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
-  if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(mbar)) : "memory");
+  if (tid == 32) {
+    for (int i = 0; i < kStages; i++) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar_wfull(i)) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar_wempty(i)) : "memory");
+    }
+    for (int s = 0; s < kSlots; s++) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar_accfull(s)) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar_aready(s)), "r"(kEpiWarps * 32) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar_obsfull(s)) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar_epsfull(s)) : "memory");
+    }
+    *abort_flag = 0;
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
-  // linear 16-byte cp.async copy of a layer's packed weight image into sW (+ its bias into the parity buffer): all 32 vectors of a
-  // thread are in flight at once, and the copy of layer l+1 overlaps the epilogue of layer l (sW is free once layer l's MMAs retired)
-  auto stage_layer = [&](int layer) {
-    const int K = (layer == 0) ? kInPad : kHid;
-    const int N = (layer == 3) ? kOutPad : kHid;
-    const char* src = reinterpret_cast<const char*>(P.w[layer]);
-    const uint32_t dst = smem_u32(sW);
-    const int nvec = N * K * 2 / 16;
-    for (int i = tid; i < nvec; i += kThreads)
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst + 16u * (uint32_t)i), "l"(src + 16 * (size_t)i) : "memory");
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
-    float* sb = sBias2 + (layer & 1) * kHid;
-    const int nb = (layer == 3) ? P.act_dim : kHid;
-    for (int i = tid; i < kHid; i += kThreads) sb[i] = (i < nb) ? P.b[layer][i] : 0.0f;
-  };
-
-  stage_layer(0);
-  asm volatile("griddepcontrol.wait;" ::: "memory");   // from here on the observations of the previous step are read
-  // ---- layer-0 A operand: normalised observations, bf16, K padded 54 -> 64 (this thread: features 32*half .. 32*half+31)
-  {
-#pragma unroll
-    for (int c = 0; c < 4; c++) {
-      const int k0 = 32 * half + 8 * c;
-      __align__(16) __nv_bfloat162 pk[4];
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        float x[2];
-#pragma unroll
-        for (int t = 0; t < 2; t++) {
-          const int k = k0 + 2 * j + t;
-          float val = 0.0f;
-          if (live && k < P.obs_dim) {
-            val = P.obs[(size_t)env * P.obs_dim + k];
-            if (P.rms_mean) val = fminf(fmaxf((val - P.rms_mean[k]) / sqrtf(P.rms_var[k] + 1e-8f), -10.0f), 10.0f);
-          }
-          x[t] = val;
-        }
-        pk[j] = __floats2bfloat162_rn(x[0], x[1]);
-      }
-      *reinterpret_cast<int4*>(sA + (row & 7) * 16 + (row >> 3) * 128 + (k0 >> 3) * 2048) = *reinterpret_cast<const int4*>(pk);
-    }
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // from here on the predecessor's results (observations, parameters) are read
+  for (int i = tid; i < kBiasFloats; i += kThreads) {
+    const int l = i < 3 * kHid ? i / kHid : 3, j = i - l * kHid;
+    sBias[i] = (l < 3 || j < P.act_dim) ? P.b[l][j] : 0.0f;
+  }
+  if (tid >= 64 && tid < 64 + kOutPad) {
+    const int j = tid - 64;
+    const float ls = j < P.act_dim ? P.log_std[j] : 0.0f;
+    sLogStd[j] = ls; sLogStd[kOutPad + j] = __expf(ls); sLogStd[2 * kOutPad + j] = 1.0f / __expf(2.0f * ls);
+  }
+  if (tid < kInPad) {
+    const bool on = P.rms_mean != nullptr && tid < P.obs_dim;
+    sNorm[tid] = on ? P.rms_mean[tid] : 0.0f;
+    sNorm[kInPad + tid] = on ? 1.0f / sqrtf(P.rms_var[tid] + 1e-8f) : 1.0f;
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-  const uint32_t tmem_d = *tmem_slot;
+  const uint32_t tmem_base = *tmem_slot;
 
-  float out_mean[kOutPad];
+  // tiles of this CTA: global tile t = j * gridDim.x + blockIdx.x for j = 0 .. nloc-1; slot s takes j = s, s + 2, ...
+  const int n_tiles = (P.n_env + kTile - 1) / kTile;
+  const int nloc = ((int)blockIdx.x < n_tiles) ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  int cnt[kSlots];
 #pragma unroll
-  for (int j = 0; j < kOutPad; j++) out_mean[j] = 0.0f;
-#pragma unroll 1
-  for (int layer = 0; layer < 4; layer++) {
-    float* sBias = sBias2 + (layer & 1) * kHid;
-    const int K = (layer == 0) ? kInPad : kHid;
-    const int N = (layer == 3) ? kOutPad : kHid;
-    // ---- this layer's weights and bias were put in flight (cp.async) before the previous epilogue: land them
-    asm volatile("cp.async.wait_all;\n" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy smem writes -> visible to the tensor-core proxy
-    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-    __syncthreads();
-    if (warp == 0 && lane == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-      const uint32_t idesc = umma_idesc(N);
-      const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sW);
-      for (int ks = 0; ks < K / 16; ks++) {
-        const uint64_t ad = umma_desc(a0 + ks * 2 * 2048, 2048, 128);
-        const uint64_t bd = umma_desc(b0 + ks * 2 * 128, 128, 16 * K);
-        umma_bf16(tmem_d, ad, bd, idesc, ks > 0 ? 1u : 0u);
+  for (int s = 0; s < kSlots; s++) cnt[s] = (nloc - s + 1) / 2;
+  // The MMA issuer walks the slot-steps (slot s, its u-th step = layer u % 4 of its (u / 4)-th tile) in the order u-major, s-minor; the
+  // producer streams the weight chunks in exactly that order.
+
+  if (warp == 0) {
+    // ================================================================ weight producer (one thread)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      bool ok = true;
+      for (int u = 0; ok && u < 4 * cnt[0]; u++) {
+        const int l = u & 3;
+        for (int s = 0; ok && s < kSlots; s++) {
+          if (u >= 4 * cnt[s]) continue;
+          const char* src = reinterpret_cast<const char*>(P.w[l]);
+          const int nchunk = layer_chunks(l);
+          for (int c = 0; c < nchunk; c++) {
+            if (!(ok = mbar_wait(bar_wempty(stage), phase ^ 1u, abort_flag, P.error))) break;
+            const uint32_t dst = smem_u32(smem + kOffRing + stage * kChunkBytes), fb = bar_wfull(stage);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(fb), "r"(kChunkBytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+                         "l"(src + (size_t)c * kChunkBytes), "r"(kChunkBytes), "r"(fb)
+                         : "memory");
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
       }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(mbar)) : "memory");
     }
-    {  // wait for the accumulator (phase parity alternates per layer); bounded so that a fault cannot hang the device
-      const uint32_t parity = layer & 1;
-      uint32_t ok = 0;
-      for (int spin = 0; spin < (1 << 22) && !ok; spin++) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}\n"
-            : "=r"(ok)
-            : "r"(smem_u32(mbar)), "r"(parity)
-            : "memory");
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer (one thread)
+    if (lane == 0) {
+      TRACE_DECL;
+      const int trace_region = 0; (void)trace_region;
+      int stage = 0;
+      uint32_t phase = 0;
+      bool ok = true;
+      for (int u = 0; ok && u < 4 * cnt[0]; u++) {
+        const int l = u & 3;
+        const int nchunk = layer_chunks(l), kc = layer_kc(l);
+        const uint32_t idesc = umma_idesc(layer_n(l));
+        for (int s = 0; ok && s < kSlots; s++) {
+          if (u >= 4 * cnt[s]) continue;
+          TRACE(s, 100 + l);
+          if (!(ok = mbar_wait(bar_aready(s), (uint32_t)(u & 1), abort_flag, P.error))) break;   // this layer's A operand is in smem, TMEM is drained
+          TRACE(s, 110 + l);
+          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+          const uint32_t a0 = smem_u32(smem + s * kABytes), tmem_d = tmem_base + (uint32_t)(s * kHid);
+          for (int c = 0; c < nchunk; c++) {
+            if (!(ok = mbar_wait(bar_wfull(stage), phase, abort_flag, P.error))) break;
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            const uint32_t b0 = smem_u32(smem + kOffRing + stage * kChunkBytes);
+            for (int ks = 0; ks < kc / 16; ks++) {
+              const int kk = c * kc + ks * 16;
+              const uint64_t ad = umma_desc(a0 + (uint32_t)(kk >> 3) * 2048u, 2048, 128);
+              const uint64_t bd = umma_desc(b0 + (uint32_t)ks * 256u, 128, 16 * kc);
+              umma_bf16(tmem_d, ad, bd, idesc, (c | ks) ? 1u : 0u);
+            }
+            umma_commit(bar_wempty(stage));   // the ring stage is free once these MMAs have read it
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
+          if (ok) umma_commit(bar_accfull(s));
+          TRACE(s, 120 + l);
+        }
       }
-      if (!ok && P.error) *P.error = 1;
     }
-    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-    if (layer < 3) stage_layer(layer + 1);
-    // ---- epilogue: this thread's row, its half of the columns
-    if (layer < 3) {
-#pragma unroll 1
-      for (int cb = 0; cb < kHid / 2; cb += 32) {
-        const int col0 = half * (kHid / 2) + cb;
-        uint32_t v[32];
-        tmem_ld32(tmem_d + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)col0, v);
+  } else {
+    // ================================================================ epilogue group of slot s (4 warps, thread <-> env row of the tile)
+    const int s = (warp - 2) / kEpiWarps;
+    const int quad = warp & 3;                       // a warp may only touch TMEM lanes 32 * (warp % 4) .. + 31
+    const int row = 32 * quad + lane;
+    const int gt = 32 * ((warp - 2) % kEpiWarps) + lane;   // thread index within the group
+    unsigned char* sA = smem + s * kABytes;
+    unsigned char* sArow = sA + (row & 7) * 16 + (row >> 3) * 128;
+    const uint32_t tmem_row = tmem_base + ((uint32_t)(32 * quad) << 16) + (uint32_t)(s * kHid);
+    // Global I/O of a tile is three CONTIGUOUS blocks (observations, noise, actions): they move as single bulk copies (cp.async.bulk)
+    // through shared-memory staging, and a thread then reads / writes its own row there. (Thread-per-row access to global memory costs
+    // one sector per lane per instruction: 3 us of load-issue time per tile for the noise alone.) Staging: observations in the part of
+    // the slot's A buffer that layer 0 does not read (bytes 16384 ..), actions in its last 16 KB (both free between tiles), noise in
+    // a buffer of its own (prefetched a whole tile ahead). A block that is not 16-byte aligned / sized (odd batch sizes) falls back to
+    // thread-per-row access.
+    const int od = P.obs_dim, ad = P.act_dim;
+    float* sObs = reinterpret_cast<float*>(sA + kInPad * kTile * 2);
+    float* sAct = reinterpret_cast<float*>(sA + kABytes - 16384);
+    float* sEps = reinterpret_cast<float*>(smem + kOffEps + s * kEpsBytes);
+    const bool obs_al = (reinterpret_cast<uintptr_t>(P.obs) & 15) == 0 && ((kTile * od * 4) & 15) == 0;
+    const bool eps_al = (reinterpret_cast<uintptr_t>(P.eps) & 15) == 0 && ((kTile * ad * 4) & 15) == 0 && ad <= kEpsCols;
+    const bool act_al = (reinterpret_cast<uintptr_t>(P.act) & 15) == 0 && ((kTile * ad * 4) & 15) == 0 && P.mean == nullptr;
+    auto tile_of = [&](int i) { return (2 * i + s) * (int)gridDim.x + (int)blockIdx.x; };
+    auto rows_of = [&](int i) { return min(kTile, P.n_env - tile_of(i) * kTile); };
+    auto bulk_load = [&](float* dst, const float* src, int bytes, uint32_t bar) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)), "l"(src),
+                   "r"(bytes), "r"(bar)
+                   : "memory");
+    };
+    uint32_t obs_phase = 0, eps_phase = 0;
+    bool ok = true;
+    TRACE_DECL;
+    const int trace_region = 1 + s; (void)trace_region;
+    if (gt == 0 && cnt[s] > 0 && obs_al && ((rows_of(0) * od * 4) & 15) == 0)
+      bulk_load(sObs, P.obs + (size_t)tile_of(0) * kTile * od, rows_of(0) * od * 4, bar_obsfull(s));
+    for (int i = 0; ok && i < cnt[s]; i++) {
+      const int tile = tile_of(i);
+      const int env = tile * kTile + row;
+      const bool live = env < P.n_env;
+      const int rows_valid = rows_of(i);
+      const bool obs_bulk = obs_al && ((rows_valid * od * 4) & 15) == 0;
+      const bool eps_bulk = eps_al && ((rows_valid * ad * 4) & 15) == 0;
+      const bool act_bulk = act_al && ((rows_valid * ad * 4) & 15) == 0;
+      if (gt == 0) TRACE(s, 200);
+      // the noise of this tile: needed after the output layer (the previous tile's readers passed the group barrier below)
+      if (gt == 0 && eps_bulk) bulk_load(sEps, P.eps + (size_t)tile * kTile * ad, rows_valid * ad * 4, bar_epsfull(s));
+      // ---- layer-0 A operand: normalised observations, bf16, K padded to 64
+      {
+        float xin[kInPad];                           // this env's observation row (zero beyond obs_dim / the batch)
+        if (obs_bulk) {
+          ok = mbar_wait(bar_obsfull(s), obs_phase, abort_flag, P.error);
+          obs_phase ^= 1u;
+          const float* orow = sObs + row * od;        // shared memory (bank = 22 * lane + k for obs_dim 54: two-way conflicts at worst)
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
+          for (int k = 0; k < kInPad; k++) xin[k] = (k < od) ? orow[k] : 0.0f;
+        } else {
+          const float* orow = P.obs + (size_t)(live ? env : 0) * od;
+#pragma unroll
+          for (int k = 0; k < kInPad; k++) xin[k] = (k < od) ? __ldg(orow + k) : 0.0f;
+        }
+        if (gt == 0) TRACE(s, 202);
+        const bool norm = P.rms_mean != nullptr;
+#pragma unroll
+        for (int g = 0; g < kInPad / 8; g++) {
           __align__(16) __nv_bfloat162 pk[4];
 #pragma unroll
           for (int j = 0; j < 4; j++) {
-            const int cc = 8 * c + 2 * j;
-            const float y0 = tanh_fast(__uint_as_float(v[cc]) + sBias[col0 + cc]);
-            const float y1 = tanh_fast(__uint_as_float(v[cc + 1]) + sBias[col0 + cc + 1]);
-            pk[j] = __floats2bfloat162_rn(y0, y1);
+            const int k = 8 * g + 2 * j;
+            float x0 = xin[k], x1 = xin[k + 1];
+            if (norm) {
+              x0 = fminf(fmaxf((x0 - sNorm[k]) * sNorm[kInPad + k], -10.0f), 10.0f);
+              x1 = fminf(fmaxf((x1 - sNorm[k + 1]) * sNorm[kInPad + k + 1], -10.0f), 10.0f);
+            }
+            pk[j] = __floats2bfloat162_rn(live ? x0 : 0.0f, live ? x1 : 0.0f);
           }
-          const int k0 = col0 + 8 * c;
-          *reinterpret_cast<int4*>(sA + (row & 7) * 16 + (row >> 3) * 128 + (k0 >> 3) * 2048) = *reinterpret_cast<const int4*>(pk);
+          *reinterpret_cast<int4*>(sArow + g * 2048) = *reinterpret_cast<const int4*>(pk);
         }
       }
-    } else if (half == 0) {
-      uint32_t v[32];
-      tmem_ld32(tmem_d + ((uint32_t)(32 * (warp & 3)) << 16), v);
+      if (gt == 0) {
+        TRACE(s, 204);
+        asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");   // the previous tile's action store has read its staging
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");   // (this thread's TMEM reads of the previous tile are done)
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");        // generic-proxy smem writes -> visible to the tensor-core proxy
+      mbar_arrive(bar_aready(s));
+      if (gt == 0) TRACE(s, 201);
+#pragma unroll 1
+      for (int l = 0; l < 4; l++) {
+        const int u = 4 * i + l;
+        ok = mbar_wait(bar_accfull(s), (uint32_t)(u & 1), abort_flag, P.error) && ok;
+        ok = __all_sync(0xffffffffu, ok);
+        if (!ok) break;
+        if (gt == 0) TRACE(s, 210 + l);
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        if (l < 3) {
+          const float* bias = sBias + l * kHid;
+#pragma unroll 1
+          for (int cb = 0; cb < kHid; cb += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_row + (uint32_t)cb, v);
 #pragma unroll
-      for (int j = 0; j < kOutPad; j++) out_mean[j] = __uint_as_float(v[j]) + sBias[j];
-    }
-  }
-  // ---- sample, log-prob (train_ppo.py:121-126,135-140), store
-  if (half == 0 && live) {
-    float lp = 0.0f;
+            for (int c = 0; c < 4; c++) {
+              __align__(16) __nv_bfloat162 pk[4];
+              const float4 b0 = *reinterpret_cast<const float4*>(bias + cb + 8 * c), b1 = *reinterpret_cast<const float4*>(bias + cb + 8 * c + 4);
+              pk[0] = __floats2bfloat162_rn(tanh_fast(__uint_as_float(v[8 * c + 0]) + b0.x), tanh_fast(__uint_as_float(v[8 * c + 1]) + b0.y));
+              pk[1] = __floats2bfloat162_rn(tanh_fast(__uint_as_float(v[8 * c + 2]) + b0.z), tanh_fast(__uint_as_float(v[8 * c + 3]) + b0.w));
+              pk[2] = __floats2bfloat162_rn(tanh_fast(__uint_as_float(v[8 * c + 4]) + b1.x), tanh_fast(__uint_as_float(v[8 * c + 5]) + b1.y));
+              pk[3] = __floats2bfloat162_rn(tanh_fast(__uint_as_float(v[8 * c + 6]) + b1.z), tanh_fast(__uint_as_float(v[8 * c + 7]) + b1.w));
+              *reinterpret_cast<int4*>(sArow + ((cb >> 3) + c) * 2048) = *reinterpret_cast<const int4*>(pk);
+            }
+          }
+          asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+          asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+          mbar_arrive(bar_aready(s));
+          if (gt == 0) TRACE(s, 220 + l);
+        } else {
+          // ---- output layer: the slot's A buffer is free (its last reader, the layer-3 MMAs, retired): the next tile's observations
+          // start to arrive while this tile samples
+          if (gt == 0 && i + 1 < cnt[s] && obs_al && ((rows_of(i + 1) * od * 4) & 15) == 0)
+            bulk_load(sObs, P.obs + (size_t)tile_of(i + 1) * kTile * od, rows_of(i + 1) * od * 4, bar_obsfull(s));
+          // mean -> sample, log-prob (train_ppo.py:121-126,135-140), store
+          uint32_t v[32];
+          tmem_ld32(tmem_row, v);
+          float e[kOutPad], a_out[kOutPad];
+          if (eps_bulk) {
+            ok = mbar_wait(bar_epsfull(s), eps_phase, abort_flag, P.error);
+            eps_phase ^= 1u;
+            const float* erow = sEps + row * ad;      // shared memory (odd row stride: conflict-free)
 #pragma unroll
-    for (int j = 0; j < kOutPad; j++) {
-      if (j < P.act_dim) {
-        const float ls = P.log_std[j];
-        const float e = P.eps[(size_t)env * P.act_dim + j];
-        const float a = out_mean[j] + __expf(ls) * e;
-        P.act[(size_t)env * P.act_dim + j] = a;
-        if (P.mean) P.mean[(size_t)env * P.act_dim + j] = out_mean[j];
-        const float d = a - out_mean[j];
-        lp += d * d / __expf(2.0f * ls) + 2.0f * ls + 1.8378770664093453f;
+            for (int j = 0; j < kOutPad; j++) e[j] = (j < ad) ? erow[j] : 0.0f;
+          } else {
+            const float* erow = P.eps + (size_t)(live ? env : 0) * ad;
+#pragma unroll
+            for (int j = 0; j < kOutPad; j++) e[j] = (j < ad) ? __ldg(erow + j) : 0.0f;
+          }
+          float lp = 0.0f;
+          const float* bias = sBias + 3 * kHid;
+#pragma unroll
+          for (int j = 0; j < kOutPad; j++) {
+            const float mu = __uint_as_float(v[j]) + bias[j];
+            const float a = mu + sLogStd[kOutPad + j] * e[j];
+            const float d = a - mu;
+            if (j < ad) lp += d * d * sLogStd[2 * kOutPad + j] + 2.0f * sLogStd[j] + 1.8378770664093453f;
+            a_out[j] = a;
+            v[j] = __float_as_uint(mu);
+          }
+          if (act_bulk) {
+            float* arow = sAct + row * ad;
+#pragma unroll
+            for (int j = 0; j < kOutPad; j++) if (j < ad) arow[j] = a_out[j];
+          } else if (live) {
+            float* arow = P.act + (size_t)env * ad;
+#pragma unroll
+            for (int j = 0; j < kOutPad; j++) if (j < ad) arow[j] = a_out[j];
+          }
+          if (live) {
+            if (P.mean) {
+#pragma unroll
+              for (int j = 0; j < kOutPad; j++) if (j < ad) P.mean[(size_t)env * ad + j] = __uint_as_float(v[j]);
+            }
+            P.logp[env] = -0.5f * lp;
+          }
+          asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+          asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");        // staged actions -> visible to the bulk store
+          asm volatile("bar.sync %0, %1;\n" ::"r"(1 + s), "r"(kEpiWarps * 32) : "memory");   // the group: noise consumed, actions staged
+          if (gt == 0 && act_bulk) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(P.act + (size_t)tile * kTile * ad),
+                         "r"(smem_u32(sAct)), "r"(rows_valid * ad * 4)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+          }
+          if (gt == 0) TRACE(s, 223);
+        }
       }
     }
-    P.logp[env] = -0.5f * lp;
+    if (gt == 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
 }
 
-// W [K, N] row-major float32 (x @ W convention) -> bf16 image of B = W^T in the canonical K-major layout, zero padded to [Np, Kp]
+// W [K, N] row-major float32 (x @ W convention) -> bf16 image of B = W^T, zero padded to [Np, Kp], as Kp / Kc chunks of 16 KB, each the
+// canonical K-major layout of Kc = 16384 / (2 Np) columns of K (32 for the hidden layers, 256 for the output layer)
 __global__ void pack_weight_kernel(const float* __restrict__ w, int K, int N, int Kp, int Np, __nv_bfloat16* __restrict__ out) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= Np * Kp) return;
   const int n = idx / Kp, k = idx % Kp;
+  const int Kc = kChunkBytes / (2 * Np), chunk = k / Kc, kk = k % Kc;
   const float v = (n < N && k < K) ? w[(size_t)k * N + n] : 0.0f;
-  const size_t byte = (size_t)(n & 7) * 16 + (size_t)(n >> 3) * (Kp / 8) * 128 + (size_t)(k >> 3) * 128 + (size_t)(k & 7) * 2;
+  const size_t byte = (size_t)chunk * kChunkBytes + (size_t)(n & 7) * 16 + (size_t)(n >> 3) * (Kc / 8) * 128 + (size_t)(kk >> 3) * 128 + (size_t)(kk & 7) * 2;
   out[byte / 2] = __float2bfloat16_rn(v);
 }
 
@@ -360,6 +583,16 @@ int mjxb_ffma_peak(int32_t device, float* tflops_out, float* ms_out) {
   return MJXB_OK;
 }
 
+#if MJXB_POLICY_TRACE
+int mjxb_policy_trace(unsigned long long* host_out) {   // profiling variant only (not part of include/mjxb.h)
+  cudaDeviceSynchronize();
+  const int rc = cudaMemcpyFromSymbol(host_out, mjxbp::g_trace, sizeof(unsigned long long) * 4096) == cudaSuccess ? 0 : MJXB_ECUDA;
+  static unsigned long long zeros[4096];
+  cudaMemcpyToSymbol(mjxbp::g_trace, zeros, sizeof(zeros));
+  return rc;
+}
+#endif
+
 int mjxb_tanh_bwd_colsum(int32_t n, int32_t c, const float* dy, const float* y, float* dz, float* db_zeroed, void* stream) {
   if (n <= 0 || c <= 0 || !dy || !db_zeroed || (y != nullptr && dz == nullptr)) return MJXB_EINVAL;
   int grid = (n + 63) / 64;
@@ -381,6 +614,8 @@ int mjxb_gae(int32_t rollout_length, int32_t n_env, const float* reward, const f
 
 int mjxb_policy_pack_weight(const float* w, int32_t k, int32_t n, int32_t k_pad, int32_t n_pad, void* out_bf16, void* stream) {
   if (!w || !out_bf16 || k <= 0 || n <= 0 || k_pad < k || n_pad < n || (k_pad % 16) || (n_pad % 16)) return MJXB_EINVAL;
+  // the image is a sequence of 16 KB chunks (Kc = 8192 / n_pad columns of K each): the two shapes the kernel streams
+  if (!((n_pad == mjxbp::kHid && k_pad % 32 == 0) || (n_pad == mjxbp::kOutPad && k_pad == mjxbp::kHid))) return MJXB_EUNSUPPORTED;
   const int total = n_pad * k_pad;
   g_mjxb_launches++;
   mjxbp::pack_weight_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, k, n, k_pad, n_pad, (__nv_bfloat16*)out_bf16);
@@ -393,9 +628,11 @@ int mjxb_policy_act(int32_t n_env, int32_t obs_dim, int32_t act_dim, const float
   if (n_env <= 0 || !obs || !w_packed || !bias || !log_std || !eps || !act || !logp) return MJXB_EINVAL;
   if (obs_dim <= 0 || obs_dim > mjxbp::kInPad || act_dim <= 0 || act_dim > mjxbp::kOutPad) return MJXB_EUNSUPPORTED;
   if ((rms_mean == nullptr) != (rms_var == nullptr)) return MJXB_EINVAL;
+  int sms = 0;
   {  // the opt-in shared-memory size is a per-device function attribute: set it once per device, thread-safely
     static std::mutex mu;
     static bool attr_set[64] = {};
+    static int num_sms[64] = {};
     int devid = 0;
     if (cudaGetDevice(&devid) != cudaSuccess || devid < 0 || devid >= 64) { cudaGetLastError(); return MJXB_ECUDA; }
     std::lock_guard<std::mutex> lock(mu);
@@ -404,8 +641,13 @@ int mjxb_policy_act(int32_t n_env, int32_t obs_dim, int32_t act_dim, const float
         cudaGetLastError();
         return MJXB_ECUDA;
       }
+      if (cudaDeviceGetAttribute(&num_sms[devid], cudaDevAttrMultiProcessorCount, devid) != cudaSuccess || num_sms[devid] <= 0) {
+        cudaGetLastError();
+        return MJXB_ECUDA;
+      }
       attr_set[devid] = true;
     }
+    sms = num_sms[devid];
   }
   mjxbp::PolicyArgs P;
   P.n_env = n_env; P.obs_dim = obs_dim; P.act_dim = act_dim; P.obs = obs; P.rms_mean = rms_mean; P.rms_var = rms_var;
@@ -414,7 +656,9 @@ int mjxb_policy_act(int32_t n_env, int32_t obs_dim, int32_t act_dim, const float
     P.w[i] = w_packed[i]; P.b[i] = bias[i];
   }
   P.log_std = log_std; P.eps = eps; P.act = act; P.logp = logp; P.mean = mean; P.error = error_flag;
-  const int grid = (n_env + mjxbp::kTile - 1) / mjxbp::kTile;
+  // persistent: one CTA per SM, each walks its env tiles two at a time (a batch of <= 148 tiles runs one tile per CTA)
+  int grid = (n_env + mjxbp::kTile - 1) / mjxbp::kTile;
+  if (grid > sms) grid = sms;
   g_mjxb_launches++;
   mjxb::launch_pdl(mjxbp::policy_act_kernel, dim3(grid), dim3(mjxbp::kThreads), (size_t)mjxbp::kSmemBytes, (cudaStream_t)stream, P);
   return cudaGetLastError() == cudaSuccess ? MJXB_OK : MJXB_ECUDA;

@@ -62,6 +62,28 @@ def test_fused_policy_without_normalisation_and_repacking():
     assert not torch.allclose(m1, m2)
 
 
+def test_fused_policy_unaligned_slices_and_many_tiles():
+    """The kernel moves a tile's observations / noise / actions as single bulk copies when the blocks are 16-byte aligned and sized, and
+    falls back to thread-per-row access otherwise: batch slices that start at an odd row (8-byte aligned only) and a batch of more than
+    2 x 148 tiles (every CTA walks several tiles in both of its slots) must give the same numbers as the aligned call."""
+    od, nu = 54, 21
+    g, params, log_std = _setup(11)
+    fp = PL.FusedPolicy(params, log_std, od, nu)
+    n = 148 * 128 * 2 + 128 * 37 + 5
+    obs_big = torch.randn(n + 1, od, device="cuda", generator=g)
+    eps_big = torch.randn(n + 1, nu, device="cuda", generator=g)
+    act_big = torch.empty(n + 1, nu, device="cuda")
+    rm, rv = torch.zeros(od, device="cuda"), torch.ones(od, device="cuda")
+    a0, lp0 = fp.act(obs_big[:n].contiguous(), eps_big[:n].contiguous(), rm, rv)
+    x = torch.clamp((obs_big[:n] - rm) / torch.sqrt(rv + 1e-8), -10, 10)
+    torch.testing.assert_close(a0, P._mlp_apply(params, x, 3) + torch.exp(log_std) * eps_big[:n], rtol=0, atol=3e-2)
+    a1, lp1 = fp.act(obs_big[1:], eps_big[1:], rm, rv, act_out=act_big[1:])       # all three blocks start 8 bytes off a 16-byte boundary
+    a2, lp2 = fp.act(obs_big[1:].contiguous(), eps_big[1:].contiguous(), rm, rv)
+    torch.cuda.synchronize()
+    assert int(fp.error) == 0
+    assert torch.equal(a1, a2) and torch.equal(lp1, lp2)
+
+
 def test_unsupported_shape_is_refused():
     g = torch.Generator(device="cuda").manual_seed(0)
     params = [p.detach() for p in P._mlp_params(54, [(128, "tanh")] * 3, 21, g, "cuda")]
