@@ -65,6 +65,7 @@ struct Tuning {
   bool inline_reset = false, sync_tiers = false, spec_reset = true;
   bool host_direct = true, direct_obs = true, direct_scalars = true;
   int host_chunks = 0;
+  bool balance_rounds = true;
   int sort_min_env = 16384;  // work-sorted scheduling from this batch size on (0 = never); MJXB_SORT_MIN_ENV
   int sort_seg_shift = 15;   // segment = 2^shift envs (one sort CTA each); the host pipeline uses its input-chunk size instead
 };
@@ -202,6 +203,11 @@ int launch(const mjxb_model* m, const StepArgs& args_in, bool dbg, cudaStream_t 
   int warps = m->warps;
   const int per_sm = (args.n_env + m->num_sms - 1) / m->num_sms;
   if (per_sm < warps) warps = per_sm < 1 ? 1 : per_sm;
+  else if (m->tune.balance_rounds) {   // a batch of a few rounds: equal rounds (4096 envs: 2 x 14 warps per SM, not 16 + 12) -- fewer warps share the SM
+    const int rounds = (per_sm + warps - 1) / warps;
+    const int bal = (per_sm + rounds - 1) / rounds;
+    if (bal < warps) warps = bal;
+  }
   int grid = (args.n_env + warps - 1) / warps;
   if (grid > m->num_sms) grid = m->num_sms;
   const bool ls_ = m->host.ls_exact != 0 && m->host.solver == 2;
@@ -358,6 +364,7 @@ int mjxb_model_create_ex(const void* blob, size_t blob_bytes, const mjxb_env_con
   m->tune.host_chunks = env_int("MJXB_HOST_CHUNKS", 0);
   m->tune.sort_min_env = (flags & MJXB_FLAG_NO_WORK_SORT) ? 0 : env_int("MJXB_SORT_MIN_ENV", m->tune.sort_min_env);
   m->tune.sort_seg_shift = env_int("MJXB_SORT_SEG_SHIFT", m->tune.sort_seg_shift);
+  m->tune.balance_rounds = env_int("MJXB_BALANCE_ROUNDS", 1) != 0;
   m->tune.host_direct = env_int("MJXB_HOST_DIRECT", 1) != 0;
   m->tune.direct_obs = env_int("MJXB_DIRECT_OBS", 1) != 0;
   m->tune.direct_scalars = env_int("MJXB_DIRECT_SCALARS", 1) != 0;

@@ -588,7 +588,9 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
     bool valid;
     int env;
     if (!reset_phase) {
-      const int item = (round * gridDim.x + blockIdx.x) * nslot + wslot;
+      // sorted schedule: odd rounds deal the groups to the CTAs in reverse, so that a CTA's heavy groups are paired with light ones
+      const int cta = (A.perm != nullptr && (round & 1)) ? (int)gridDim.x - 1 - (int)blockIdx.x : (int)blockIdx.x;
+      const int item = (round * gridDim.x + cta) * nslot + wslot;
       valid = item < n_items;
       env = valid ? (consuming ? A.in_list[item] : (A.perm != nullptr ? A.perm[item] : item)) : (consuming ? A.in_list[0] : 0);
     } else {
