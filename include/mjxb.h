@@ -209,6 +209,11 @@ int mjxb_tanh_bwd_colsum(int32_t n, int32_t c, const float* dy, const float* y, 
 int mjxb_ppo_loss(int32_t n, int32_t act_dim, const float* mean, const float* log_std, const float* action, const float* old_logp,
                   const float* adv, float clip_eps, float ent_coef, float* scratch4, float* g_mean, float* g_log_std, float* loss_out,
                   void* stream);
+/* the same for a mean / g_mean stored with a row stride of ld_mean >= act_dim floats (an output layer padded to a multiple of four
+ * columns so that its GEMMs take the aligned tensor-core kernels); the padding columns of g_mean are written as zeros */
+int mjxb_ppo_loss_ld(int32_t n, int32_t act_dim, int32_t ld_mean, const float* mean, const float* log_std, const float* action,
+                     const float* old_logp, const float* adv, float clip_eps, float ent_coef, float* scratch4, float* g_mean,
+                     float* g_log_std, float* loss_out, void* stream);
 /* Adam (optax.adam semantics: bias-corrected moments, eps outside the square root) over one flat parameter / gradient buffer of n floats:
  * elements [0, split) use lr0, the rest lr1; grad is multiplied by grad_scale first (1 / world size after an all-reduce sum);
  * *step_dev (device float, 0 at the start) counts the updates, so the call can be replayed from a CUDA graph. */

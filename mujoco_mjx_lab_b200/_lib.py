@@ -24,7 +24,7 @@ SYMBOLS = ("mjxb_abi_version", "mjxb_launch_count", "mjxb_blob_sizeof", "mjxb_en
            "mjxb_model_create", "mjxb_model_create_ex", "mjxb_model_flags", "mjxb_model_reserve", "mjxb_ffma_peak", "mjxb_model_destroy", "mjxb_model_dims", "mjxb_model_scratch_bytes", "mjxb_launch_config", "mjxb_reset", "mjxb_step",
            "mjxb_step_autoreset", "mjxb_physics_step", "mjxb_forward", "mjxb_speed_test", "mjxb_reset_host", "mjxb_step_host",
            "mjxb_step_autoreset_host", "mjxb_state_get_host", "mjxb_state_set_host", "mjxb_policy_pack_weight", "mjxb_policy_act", "mjxb_gae", "mjxb_tanh_bwd_colsum",
-           "mjxb_step_fwd_tape", "mjxb_step_vjp", "mjxb_ppo_loss", "mjxb_adam",
+           "mjxb_step_fwd_tape", "mjxb_step_vjp", "mjxb_ppo_loss", "mjxb_ppo_loss_ld", "mjxb_adam",
            "mjxb_comm_create", "mjxb_comm_local_handles", "mjxb_comm_connect", "mjxb_comm_grad_buffer", "mjxb_comm_error",
            "mjxb_allreduce_adam", "mjxb_comm_destroy")
 
@@ -98,6 +98,7 @@ def lib(variant: str = "fast") -> C.CDLL:
     L.mjxb_tanh_bwd_colsum.argtypes = [i32, i32, vp, vp, vp, vp, vp]
     f32 = C.c_float
     L.mjxb_ppo_loss.argtypes = [i32, i32, vp, vp, vp, vp, vp, f32, f32, vp, vp, vp, vp, vp]
+    L.mjxb_ppo_loss_ld.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp, f32, f32, vp, vp, vp, vp, vp]
     L.mjxb_adam.argtypes = [i32, i32, vp, vp, vp, vp, vp, f32, f32, f32, f32, f32, f32, vp]
     L.mjxb_comm_create.argtypes = [i32, i32, i32, C.POINTER(vp)]
     L.mjxb_comm_local_handles.argtypes = [vp, vp]

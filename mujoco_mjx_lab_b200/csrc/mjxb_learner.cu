@@ -32,7 +32,7 @@ __global__ void adv_stats_kernel(int n, const float* __restrict__ adv, float* __
 }
 
 // one thread per sample: logp, ratio, clipped surrogate, d loss / d mean; block-reduced d loss / d log_std and loss sums
-__global__ void ppo_loss_kernel(int n, int A, const float* __restrict__ mean, const float* __restrict__ log_std, const float* __restrict__ action,
+__global__ void ppo_loss_kernel(int n, int A, int ld, const float* __restrict__ mean, const float* __restrict__ log_std, const float* __restrict__ action,
                                 const float* __restrict__ old_logp, const float* __restrict__ adv, const float* __restrict__ stats, float clip_eps,
                                 float ent_coef, float* __restrict__ g_mean, float* __restrict__ g_log_std, float* __restrict__ loss_out) {
   __shared__ float s_ls[kMaxAct], s_ivar[kMaxAct], s_gls[kMaxAct];
@@ -58,7 +58,7 @@ __global__ void ppo_loss_kernel(int n, int A, const float* __restrict__ mean, co
     for (int j = 0; j < kMaxAct; j++) {
       d[j] = 0.f;
       if (j < A) {
-        d[j] = action[(size_t)i * A + j] - mean[(size_t)i * A + j];
+        d[j] = action[(size_t)i * A + j] - mean[(size_t)i * ld + j];
         q += d[j] * d[j] * s_ivar[j] + 2.0f * s_ls[j] + 1.8378770664093453f;     // log(2 pi)
       }
     }
@@ -77,8 +77,10 @@ __global__ void ppo_loss_kernel(int n, int A, const float* __restrict__ mean, co
     for (int j = 0; j < kMaxAct; j++)
       if (j < A) {
         const float t = d[j] * s_ivar[j];
-        g_mean[(size_t)i * A + j] = dlogp * t;               // d logp / d mean_j = (a_j - mean_j) / var_j
+        g_mean[(size_t)i * ld + j] = dlogp * t;              // d logp / d mean_j = (a_j - mean_j) / var_j
         gls[j] = dlogp * (d[j] * t - 1.0f);                  // d logp / d log_std_j = (a_j - mean_j)^2 / var_j - 1
+      } else if (j < ld) {
+        g_mean[(size_t)i * ld + j] = 0.0f;                   // padding columns of a padded output layer carry no gradient
       }
   }
   // block reduction of the log_std gradient and the loss
@@ -128,7 +130,14 @@ extern "C" {
 int mjxb_ppo_loss(int32_t n, int32_t act_dim, const float* mean, const float* log_std, const float* action, const float* old_logp,
                   const float* adv, float clip_eps, float ent_coef, float* scratch4, float* g_mean, float* g_log_std, float* loss_out,
                   void* stream_) {
-  if (n <= 0 || act_dim <= 0 || act_dim > mjxbl::kMaxAct || !mean || !log_std || !action || !old_logp || !adv || !scratch4 || !g_mean ||
+  return mjxb_ppo_loss_ld(n, act_dim, act_dim, mean, log_std, action, old_logp, adv, clip_eps, ent_coef, scratch4, g_mean, g_log_std, loss_out,
+                          stream_);
+}
+
+int mjxb_ppo_loss_ld(int32_t n, int32_t act_dim, int32_t ld_mean, const float* mean, const float* log_std, const float* action,
+                     const float* old_logp, const float* adv, float clip_eps, float ent_coef, float* scratch4, float* g_mean, float* g_log_std,
+                     float* loss_out, void* stream_) {
+  if (n <= 0 || act_dim <= 0 || act_dim > mjxbl::kMaxAct || ld_mean < act_dim || ld_mean > mjxbl::kMaxAct || !mean || !log_std || !action || !old_logp || !adv || !scratch4 || !g_mean ||
       !g_log_std || !loss_out) return MJXB_EINVAL;
   cudaStream_t stream = (cudaStream_t)stream_;
   cudaError_t e = cudaMemsetAsync(scratch4, 0, 4 * sizeof(float), stream);
@@ -137,7 +146,7 @@ int mjxb_ppo_loss(int32_t n, int32_t act_dim, const float* mean, const float* lo
   if (e != cudaSuccess) return mjxb::report_cuda_error(e, "cudaMemsetAsync(ppo_loss)");
   int blocks = (n + 255) / 256;
   mjxbl::adv_stats_kernel<<<blocks > 592 ? 592 : blocks, 256, 0, stream>>>(n, adv, scratch4);
-  mjxbl::ppo_loss_kernel<<<(n + 127) / 128, 128, 0, stream>>>(n, act_dim, mean, log_std, action, old_logp, adv, scratch4, clip_eps, ent_coef,
+  mjxbl::ppo_loss_kernel<<<(n + 127) / 128, 128, 0, stream>>>(n, act_dim, ld_mean, mean, log_std, action, old_logp, adv, scratch4, clip_eps, ent_coef,
                                                              g_mean, g_log_std, loss_out);
   g_mjxb_launches += 2;
   e = cudaGetLastError();

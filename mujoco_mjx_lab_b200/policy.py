@@ -16,9 +16,14 @@ HID, IN_PAD, OUT_PAD = 256, 64, 32
 
 
 def supported(params: List[torch.Tensor], obs_dim: int, act_dim: int) -> bool:
+    """params: the eight weight / bias tensors; the input layer may carry zero rows beyond obs_dim and the output layer zero columns
+    beyond act_dim (the learner's padded copies, ppo.PPOTrainer): the packed image is the same."""
+    if len(params) != 8 or obs_dim > IN_PAD or act_dim > OUT_PAD:
+        return False
     shapes = [tuple(p.shape) for p in params]
-    return (len(params) == 8 and obs_dim <= IN_PAD and act_dim <= OUT_PAD and
-            shapes == [(obs_dim, HID), (HID,), (HID, HID), (HID,), (HID, HID), (HID,), (HID, act_dim), (act_dim,)])
+    k0, n3 = shapes[0][0], shapes[6][1] if len(shapes[6]) == 2 else -1
+    return (obs_dim <= k0 <= IN_PAD and act_dim <= n3 <= OUT_PAD and all(p.is_contiguous() for p in params) and
+            shapes == [(k0, HID), (HID,), (HID, HID), (HID,), (HID, HID), (HID,), (HID, n3), (n3,)])
 
 
 class FusedPolicy:
@@ -30,7 +35,7 @@ class FusedPolicy:
             raise ValueError("fused policy kernel: unsupported network shape")
         self.params, self.log_std, self.obs_dim, self.act_dim = params, log_std, obs_dim, act_dim
         dev = params[0].device
-        self.dims = [(obs_dim, HID, IN_PAD, HID), (HID, HID, HID, HID), (HID, HID, HID, HID), (HID, act_dim, HID, OUT_PAD)]
+        self.dims = [(params[0].shape[0], HID, IN_PAD, HID), (HID, HID, HID, HID), (HID, HID, HID, HID), (HID, params[6].shape[1], HID, OUT_PAD)]
         self.packed = [torch.zeros(npad * kpad, dtype=torch.bfloat16, device=dev) for (_, _, kpad, npad) in self.dims]
         self.error = torch.zeros(1, dtype=torch.int32, device=dev)
         self._w = (C.c_void_p * 4)(*[t.data_ptr() for t in self.packed])

@@ -99,15 +99,19 @@ class _PPOLoss(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, mean, log_std, action, old_logp, adv, clip_eps: float, ent_coef: float):
+        """`mean` may be wider than the action (an output layer padded to a multiple of four columns, see PPOTrainer): its first
+        action.shape[1] columns are the mean, the rest is ignored and receives a zero gradient."""
         import ctypes as C
         from . import _lib
         mean, action, old_logp, adv = mean.contiguous(), action.contiguous(), old_logp.contiguous(), adv.contiguous()
-        n, a = mean.shape
+        n, ld = mean.shape
+        a = action.shape[1]
         g_mean, g_ls = torch.empty_like(mean), torch.empty_like(log_std)
         scratch = torch.empty(5, dtype=torch.float32, device=mean.device)          # [0:4] statistics, [4] the loss
-        _lib.check(_lib.lib().mjxb_ppo_loss(n, a, mean.data_ptr(), log_std.data_ptr(), action.data_ptr(), old_logp.data_ptr(), adv.data_ptr(),
-                                            float(clip_eps), float(ent_coef), scratch.data_ptr(), g_mean.data_ptr(), g_ls.data_ptr(),
-                                            scratch[4:].data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "mjxb_ppo_loss")
+        _lib.check(_lib.lib().mjxb_ppo_loss_ld(n, a, ld, mean.data_ptr(), log_std.data_ptr(), action.data_ptr(), old_logp.data_ptr(),
+                                               adv.data_ptr(), float(clip_eps), float(ent_coef), scratch.data_ptr(), g_mean.data_ptr(),
+                                               g_ls.data_ptr(), scratch[4:].data_ptr(),
+                                               C.c_void_p(torch.cuda.current_stream().cuda_stream)), "mjxb_ppo_loss_ld")
         ctx.save_for_backward(g_mean, g_ls)
         return scratch[4]
 
@@ -246,12 +250,37 @@ class PPOTrainer:
         self.log_std = torch.full((nu,), float(cfg.log_std_init), device=self.dev, requires_grad=True)
         self.value = _mlp_params(od, cfg.value_hidden_layer_specs, 1, gen, self.dev)
         self.fused_learner = bool(use_fused_learner) and self.dev.type == "cuda" and nu <= 32
+        self.kpad = od
         if self.fused_learner:
             # every parameter is a view into ONE flat buffer and its .grad a view into one flat gradient buffer: autograd accumulates
-            # in place, the NCCL all-reduce runs on the flat gradient without a flatten / unflatten pass, Adam is one kernel
-            allp = self.policy + [self.log_std] + self.value
-            n_pol = sum(p.numel() for p in self.policy) + self.log_std.numel()
-            self.flat_p = torch.cat([p.detach().reshape(-1) for p in allp]).contiguous()
+            # in place, the NCCL all-reduce runs on the flat gradient without a flatten / unflatten pass, Adam is one kernel.
+            # The learner's copies of the input layers and of the policy's output layer are zero-padded (54 -> 64 input rows, 21 -> 32
+            # output columns): a float32 GEMM whose leading dimension is not a multiple of four falls back to cuBLAS's unaligned
+            # mma.sync kernels (tools/prof_update2.py: 0.58 ms of a 1.37 ms minibatch step); padded, every GEMM of the step runs on the
+            # tcgen05 TF32 kernels. Padding rows / columns see zero inputs / receive zero gradients, so they stay zero under Adam:
+            # the function computed is the unpadded network's (self.policy / self.value are views of the unpadded blocks).
+            def _pad(t, shape):
+                out = torch.zeros(shape, device=t.device)
+                out[tuple(slice(0, d) for d in t.shape)] = t.detach()
+                return out
+            self.kpad = ((od + 15) // 16) * 16 if od % 4 else od
+            npad = ((nu + 15) // 16) * 16 if nu % 4 else nu
+            hp, hv = self.policy[0].shape[1], self.value[0].shape[1]
+            pol_pad = [_pad(self.policy[0], (self.kpad, hp))] + self.policy[1:-2] + [_pad(self.policy[-2], (self.policy[-2].shape[0], npad)),
+                                                                                    _pad(self.policy[-1], (npad,))]
+            val_pad = [_pad(self.value[0], (self.kpad, hv))] + self.value[1:]
+            allp = pol_pad + [self.log_std] + val_pad
+            # every parameter starts on a 256-byte boundary of the flat buffer (gaps are zeros with zero gradients): a weight whose
+            # POINTER is not 16-byte aligned sends its GEMMs to the same unaligned kernels as an unaligned leading dimension
+            # (the 21-float log_std used to misalign every value-network weight behind it)
+            offs, o = [], 0
+            for p in allp:
+                offs.append(o)
+                o += ((p.numel() + 63) // 64) * 64
+            n_pol = offs[len(pol_pad) + 1]
+            self.flat_p = torch.zeros(o, device=self.dev)
+            for p, o_ in zip(allp, offs):
+                self.flat_p[o_:o_ + p.numel()] = p.detach().reshape(-1)
             self.comm = None
             if self.world > 1 and os.environ.get("MJXB_PPO_NCCL_ALLREDUCE") is None:
                 try:                                                    # peer-memory gradient exchange fused into the Adam kernel
@@ -260,14 +289,17 @@ class PPOTrainer:
                     print(f"[ppo] peer-memory communicator unavailable ({type(e).__name__}: {e}); using NCCL")
                     self.comm = None
             self.flat_g = self.comm.grad if self.comm is not None else torch.zeros_like(self.flat_p)
-            views, o = [], 0
-            for p in allp:
+            views = []
+            for p, o in zip(allp, offs):
                 v = self.flat_p[o:o + p.numel()].view(p.shape).detach().requires_grad_()
                 v.grad = self.flat_g[o:o + p.numel()].view(p.shape)
                 views.append(v)
-                o += p.numel()
             npol = len(self.policy)
-            self.policy, self.log_std, self.value = views[:npol], views[npol], views[npol + 1:]
+            self._pol_pad, self.log_std, self._val_pad = views[:npol], views[npol], views[npol + 1:]
+            # the unpadded blocks, for everything outside the minibatch step (rollout fallback, tests, checkpoints)
+            self.policy = [self._pol_pad[0].detach()[:od]] + [p.detach() for p in self._pol_pad[1:-2]] + \
+                          [self._pol_pad[-2].detach()[:, :nu], self._pol_pad[-1].detach()[:nu]]
+            self.value = [self._val_pad[0].detach()[:od]] + [p.detach() for p in self._val_pad[1:]]
             self.opt = _FlatAdam(self.flat_p, self.flat_g, n_pol, cfg.lr_policy, cfg.lr_value, comm=self.comm)
             self.opt_p = self.opt_v = None
         else:
@@ -292,13 +324,13 @@ class PPOTrainer:
         self.fused = None
         if use_fused_policy and self.dev.type == "cuda":
             from . import policy as _policy
-            flat = [p.detach() for p in self.policy]
+            flat = [p.detach() for p in (self._pol_pad if self.fused_learner else self.policy)]   # (zero-padded or not: same image)
             if _policy.supported(flat, od, nu) and all(a == "tanh" for _, a in cfg.policy_hidden_layer_specs):
                 self.fused = _policy.FusedPolicy(flat, self.log_std.detach(), od, nu)
         self.graph = None
         self.upd = None
         self.use_graph = use_cuda_graph
-        self.n_grads = sum(p.numel() for p in self.policy + [self.log_std] + self.value)
+        self.n_grads = self.flat_p.numel() if self.fused_learner else sum(p.numel() for p in self.policy + [self.log_std] + self.value)
         self.timing: Dict[str, float] = {}
 
     # ---------------------------------------------------------------- rollout (train_ppo.py:128-169)
@@ -413,9 +445,9 @@ class PPOTrainer:
         o, a, olp, r_, ad = obs_f[idx], act_f[idx], logp_f[idx], ret_f[idx], adv_f[idx]
         if zero:
             self._zero_grads()
-        mean = _mlp_apply(self.policy, o, self.nh_p)
+        mean = _mlp_apply(self._pol_pad if self.fused_learner else self.policy, o, self.nh_p)
         if self.fused_learner:
-            loss = _PPOLoss.apply(mean, self.log_std, a, olp, ad, cfg.clip_eps, cfg.ent_coef)
+            loss = _PPOLoss.apply(mean, self.log_std, a, olp, ad, cfg.clip_eps, cfg.ent_coef)       # (mean: act_dim columns + padding)
         else:
             logp = gaussian_logprob(mean, self.log_std, a)
             ratio = torch.exp(logp - olp)
@@ -424,7 +456,7 @@ class PPOTrainer:
             entropy = 0.5 * torch.sum(1.0 + math.log(2.0 * math.pi) + 2.0 * self.log_std) / a.shape[-1]
             loss = loss_p - cfg.ent_coef * entropy
         loss.backward()
-        v = _mlp_apply(self.value, o, self.nh_v).squeeze(-1)
+        v = _mlp_apply(self._val_pad if self.fused_learner else self.value, o, self.nh_v).squeeze(-1)
         loss_v = torch.mean((v - r_) ** 2)
         loss_v.backward()
 
@@ -513,12 +545,19 @@ class PPOTrainer:
         od = self.obs_traj.shape[-1]
         with torch.no_grad():
             self.rms.update(self.obs_traj.reshape(-1, od), self.world)
-            obs_norm = self.rms.normalize(self.obs_traj)
-            obs_last = self.rms.normalize(self.obs)
-            stack = torch.cat([obs_norm, obs_last.unsqueeze(0)], 0).reshape((T + 1) * n, od)
-            values = _mlp_apply(self.value, stack, self.nh_v).reshape(T + 1, n)
+            if self.kpad != od:                 # normalised observations in rows of kpad floats (zero padded) for the aligned GEMMs
+                if getattr(self, "_obs_pad", None) is None:
+                    self._obs_pad = torch.zeros(T + 1, n, self.kpad, device=self.dev)
+                self._obs_pad[:, :, :od] = self.rms.normalize(self.obs_all)
+                obs_norm, stack = self._obs_pad[:T], self._obs_pad.view((T + 1) * n, self.kpad)
+                values = _mlp_apply(self._val_pad, stack, self.nh_v).reshape(T + 1, n)
+            else:
+                obs_norm = self.rms.normalize(self.obs_traj)
+                obs_last = self.rms.normalize(self.obs)
+                stack = torch.cat([obs_norm, obs_last.unsqueeze(0)], 0).reshape((T + 1) * n, od)
+                values = _mlp_apply(self.value, stack, self.nh_v).reshape(T + 1, n)
             adv, ret = self.compute_gae(self.r_traj, values, self.term_traj, self.trunc_traj)
-        obs_f, act_f = obs_norm.reshape(T * n, od), self.act_traj.reshape(T * n, -1)
+        obs_f, act_f = obs_norm.reshape(T * n, self.kpad), self.act_traj.reshape(T * n, -1)
         logp_f, adv_f, ret_f = self.logp_traj.reshape(-1), adv.reshape(-1), ret.reshape(-1)
         total = T * n
         mb = min(cfg.minibatch_size, total)
@@ -528,7 +567,7 @@ class PPOTrainer:
             # eager step is ~200 launches and is bound by their dispatch, not by the GPU
             if self.upd is None:
                 f32 = dict(dtype=torch.float32, device=self.dev)
-                self.upd = dict(obs=torch.empty(total, od, **f32), adv=torch.empty(total, **f32), ret=torch.empty(total, **f32),
+                self.upd = dict(obs=torch.empty(total, self.kpad, **f32), adv=torch.empty(total, **f32), ret=torch.empty(total, **f32),
                                 idx=torch.zeros(mb, dtype=torch.int64, device=self.dev), act=act_f, logp=logp_f, eager_steps=0,
                                 fb=None, st=None, flat=torch.zeros(self.n_grads, **f32))
             u = self.upd
