@@ -281,7 +281,7 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     traffic = None                                                # dram bytes per step launch from the committed ncu capture
     try:
-        tp = [q for q in (os.path.join(ROOT, "profiles", f) for f in ("r2_traffic.json", "r1_traffic.json")) if os.path.exists(q)]
+        tp = [q for q in (os.path.join(ROOT, "profiles", f) for f in ("r2c_traffic.json", "r2_traffic.json", "r1_traffic.json")) if os.path.exists(q)]
         tj = json.load(open(tp[0]))
         if int(tj["n_env"]) == n:
             traffic = float(tj["dram_bytes_per_launch"])
@@ -297,8 +297,9 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "api": "mjxb_step_autoreset_host (pinned host buffers; one launch, action/keys streamed in behind ready flags, outputs stored into the caller's mapped buffers)"},
         "gpu_launches": gpu_launches,
-        "gpu_launches_note": "counted by libmjxb.so (mjxb_launch_count) over the timed region: per step the main tier + two overflow tiers that exit at once when their list is empty",
-        "kernels": ["mjxb_step_kernel<false,32,16,16,true,true> (step: 32-row tile, 16 env-warps per SM, single-step instantiation)",
+        "gpu_launches_note": "counted by libmjxb.so (mjxb_launch_count) over the timed region: per step the schedule sort (batches >= 16,384 envs), the main tier and two overflow tiers that exit at once when their list is empty",
+        "kernels": ["mjxb_sort_work_kernel (work-sorted schedule: envs dealt to the CTAs by descending cost of their previous step, ~5 us)",
+                    "mjxb_step_kernel<false,32,16,16,true,true> (step: 32-row tile, 16 env-warps per SM, single-step instantiation)",
                     "mjxb_step_kernel<false,64,24,10,true,false> and <false,320,176,3,true,false> (overflow tiers; exit at once when their list is empty)"],
         "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                      "traffic": traffic, "algorithmic_bytes_per_launch": ALG_BYTES_PER_STEP * n, "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 (of fallback)",
