@@ -156,3 +156,17 @@ def test_fused_learner_equals_torch_learner(env):
         b.iteration()
         for pa, pb in zip(a.policy + [a.log_std] + a.value, b.policy + [b.log_std] + b.value):
             torch.testing.assert_close(pa, pb, rtol=2e-3, atol=2e-4)
+    # the fused learner's GEMM operands are zero-padded to aligned shapes (input layers 54 -> 64 rows, policy head 21 -> 32 columns,
+    # every parameter on a 256-byte boundary of the flat buffer): the padding must still be exactly zero after Adam steps, i.e. the
+    # function computed is the unpadded network's
+    od, nu = a.sys.obs_dim, a.sys.nu
+    assert a.kpad == 64 and a._pol_pad[0].shape == (64, 256) and a._pol_pad[-2].shape == (256, 32)
+    assert float(a._pol_pad[0][od:].abs().max()) == 0.0 and float(a._val_pad[0][od:].abs().max()) == 0.0
+    assert float(a._pol_pad[-2][:, nu:].abs().max()) == 0.0 and float(a._pol_pad[-1][nu:].abs().max()) == 0.0
+    assert all(p.data_ptr() % 256 == 0 for p in a._pol_pad + [a.log_std] + a._val_pad)
+    used = sum(p.numel() for p in a._pol_pad + [a.log_std] + a._val_pad)
+    mask = torch.ones_like(a.flat_p, dtype=torch.bool)
+    for p in a._pol_pad + [a.log_std] + a._val_pad:
+        o = (p.data_ptr() - a.flat_p.data_ptr()) // 4
+        mask[o:o + p.numel()] = False
+    assert int(mask.sum()) == a.flat_p.numel() - used and float(a.flat_p[mask].abs().max() if mask.any() else 0.0) == 0.0
