@@ -40,9 +40,12 @@ struct StepArgs {
   // deferred auto-reset: envs that finish an episode are queued per CTA and re-initialised in packed lockstep rounds after the
   // step rounds (a reset run inline would make the other 15 warps of its round wait for a whole extra pass)
   int* reset_list; int reset_stride;
-  // speculative auto-reset (small batches: every SM has idle warps): the CTA runs two warps per env, one steps it, its partner
-  // re-initialises it from its key at the same time (single_reset depends on the key alone), and the partner's result is stored only
-  // if the step finished the episode -- the reset no longer runs as a second, serialised pass of the pipeline
+  // concurrent auto-reset (batches of ONE round, <= 14 envs per SM): besides its `spec_reset` stepping warps a CTA runs reset warps
+  // (blockDim / 32 - spec_reset of them). Whether an env finishes its episode in this step is known right after the stepping warp's
+  // kinematics (termination reads the pelvis height of the step's forward pass, truncation the episode counter): it is published
+  // then, and a reset warp re-initialises that env from its key (single_reset depends on the key alone) beside the step -- the reset
+  // no longer runs as a second, serialised pass of the pipeline. Reset warps without work only answer the CTA barriers. More
+  // finishing envs than reset warps in one CTA (rare): the surplus takes the deferred path below.
   int spec_reset;
   // work-sorted scheduling (large batches): `perm` lists the envs of each segment by descending predicted cost, so that the 16 envs a CTA
   // runs in lockstep need about the same number of Newton iterations; every env leaves its cost key (this step's iteration count) in
@@ -552,7 +555,11 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
   if (A.in_list == nullptr) asm volatile("griddepcontrol.wait;" ::: "memory");
   __shared__ int s_reset_count;
   __shared__ int s_spec_done[32];
-  if (threadIdx.x == 0) s_reset_count = 0;
+  __shared__ int s_spec_need[32];   // per stepping slot: 0 = the env goes on, 1 = it finishes and a reset warp serves it, 2 = finishes, unserved
+  __shared__ int s_need_slot[32];   // the slots that need a reset, in order of publication
+  __shared__ int s_pub_count, s_need_count;
+  if (threadIdx.x == 0) { s_reset_count = 0; s_pub_count = 0; s_need_count = 0; }
+  if (threadIdx.x < 32) s_spec_need[threadIdx.x] = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   using WS = WarpS<CAP, MAXCC>;
@@ -566,11 +573,11 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
   const bool consuming = A.in_list != nullptr;
   const int n_items = consuming ? *reinterpret_cast<volatile int*>(A.in_count) : A.n_env;
   const bool spec = SINGLE && A.spec_reset != 0 && A.autoreset && A.mode == MODE_ENV_STEP && !consuming;   // CTA-uniform
-  const int nslot = spec ? (nwarp >> 1) : nwarp;          // envs per CTA round
-  const int wslot = spec ? warp % nslot : warp;
-  const bool spec_partner = spec && warp >= nslot;        // this warp re-initialises env `wslot` speculatively
+  const int nslot = spec ? min(A.spec_reset, nwarp - 1) : nwarp;   // stepping warps = envs per CTA round
+  int wslot = warp;                                        // (a reset warp takes the slot of the env it serves)
+  const bool spec_warp = spec && warp >= nslot;            // this warp is a reset warp of the step round
   const int n_rounds = (n_items + gridDim.x * nslot - 1) / (gridDim.x * nslot);
-  const bool defer = A.autoreset && A.reset_list != nullptr && A.mode == MODE_ENV_STEP && !spec;
+  const bool defer = A.autoreset && A.reset_list != nullptr && A.mode == MODE_ENV_STEP;
   int total_rounds = n_rounds, n_reset = 0;
   bool reset_phase = false;
   for (int round = 0;; round++) {
@@ -583,6 +590,30 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
       if (round == total_rounds) break;
     }
     if (A.lockstep > 0 || spec) group_sync(warp, spec ? 0 : A.lockstep_group);
+    const bool spec_partner = spec_warp && !reset_phase;
+    if (spec_partner) {
+      // wait until every stepping warp of the CTA has published its verdict (~3 K cycles in: right after its kinematics), then take
+      // the (warp - nslot)-th env that needs a reset, if there is one; otherwise stay out of the SM's way and only answer the CTA
+      // barriers of the round (1024 envs: 7 instead of 14 working warps per SM)
+      int served = -1;
+      if (lane == 0) {
+        volatile int* pub = &s_pub_count;
+#pragma unroll 1
+        for (int spin = 0; spin < (1 << 20) && *pub < nslot; spin++) __nanosleep(200);
+        __threadfence_block();
+        const int k = warp - nslot;
+        if (k < *reinterpret_cast<volatile int*>(&s_need_count)) served = *reinterpret_cast<volatile int*>(&s_need_slot[k]);
+      }
+      served = __shfl_sync(FULL, served, 0);
+      if (served < 0) {
+        if (A.lockstep > 0) group_sync(warp, A.lockstep_group);                                   // solver entry
+        if (A.lockstep == 3) { while (__syncthreads_or(0)) {} }                                   // per-iteration barriers / solver exit
+        else if (A.lockstep > 0 && A.lockstep != 2) group_sync(warp, A.lockstep_group);
+        __syncthreads();                                                                          // the verdict barrier of the round's tail
+        continue;
+      }
+      wslot = served;
+    }
     // Warps without work in the last round (and envs that overflow the row tile) still run the whole pipeline -- on env 0 /
     // on a truncated row set -- with every global store suppressed, so that all warps of the CTA reach the same barriers.
     bool valid;
@@ -804,6 +835,20 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
         for (int k = 0; k < 3; k++) { S.pelvis_pos[k] = S.a.xpos[pb][k]; S.head_pos[k] = S.a.xpos[hb][k]; }
 #pragma unroll
         for (int k = 0; k < 4; k++) S.pelvis_quat[k] = S.a.xquat[pb][k];
+        if (spec && !spec_warp && !reset_phase) {   // the verdict for the reset warps: the same predicates as the env layer evaluates at the end
+          const bool fallen = S.a.xpos[pb][2] < cfg.terminate_height;
+          const float ep1 = A.in.aux[(size_t)env * MJXB_AUX_DIM + 8] + 1.0f;
+          const bool trunc = cfg.max_episode_steps > 0 && ep1 >= (float)cfg.max_episode_steps;
+          int need = 0;
+          if (valid && mode == MODE_ENV_STEP && (fallen || trunc)) {
+            const int k = atomicAdd(&s_need_count, 1);
+            s_need_slot[k] = wslot;
+            need = k < nwarp - nslot ? 1 : 2;           // more finishing envs than reset warps: deferred reset after the round
+          }
+          s_spec_need[wslot] = need;
+          __threadfence_block();
+          atomicAdd(&s_pub_count, 1);
+        }
       }
       if (DBG) {
         if (A.dbg.xpos && lane < nbody) for (int k = 0; k < 3; k++) A.dbg.xpos[((size_t)env * nbody + lane) * 3 + k] = S.a.xpos[lane][k];
@@ -1800,9 +1845,10 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
       }  // pass
       (void)tgt_x; (void)tgt_y; (void)tgt_z;
     }  // nsteps
-    if (spec) {   // the stepping warp tells its partner whether the episode ended (CTA barrier: both warps of the pair are in this CTA)
+    if (spec && !reset_phase) {   // the stepping warp tells the reset warp that served it whether the episode really ended (it does unless the env overflowed)
       if (!spec_partner && lane == 0) s_spec_done[wslot] = (valid && !overflow && deferred) ? 1 : 0;
       __syncthreads();
+      if (threadIdx.x == 0) { s_pub_count = 0; s_need_count = 0; }   // re-armed for the next step round (its round-top barrier orders this)
       if (spec_partner) {
         const bool take = valid && !overflow && s_spec_done[wslot] != 0;
         if (take) {
@@ -1835,7 +1881,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
         A.reward[env] = out_reward; A.terminated[env] = out_term; A.truncated[env] = out_trunc;
         if (A.reset_mask) A.reset_mask[env] = 1;
         if (A.status) A.status[env] = status;
-        if (!spec) {
+        if (!spec || s_spec_need[wslot] != 1) {   // (concurrent-reset rounds: only an env that no reset warp could serve)
           const int slot = atomicAdd(&s_reset_count, 1);
           A.reset_list[(size_t)blockIdx.x * A.reset_stride + slot] = env;
         }

@@ -54,15 +54,19 @@ def test_cg_solver_apg_settings():
 
 
 def test_speculative_reset_is_bit_identical(model):
-    """Small batches (two warps per env fit on every SM) run the auto-reset speculatively beside the step (mjxb_abi.cu launch()):
-    same bits as the deferred-reset path, over steps that do reset envs, at sizes on both sides of the switch-over."""
+    """Batches of one round (<= 14 envs per SM) re-initialise an env that finishes its episode with a reset warp beside the step
+    (mjxb_abi.cu launch(); the verdict is published right after the stepping warp's kinematics): same bits as the deferred-reset path,
+    over steps that do reset envs -- more of them than a CTA has reset warps, so the surplus takes the deferred path -- at sizes on
+    both sides of the switch-over."""
     import helpers
     from mujoco_mjx_lab_b200 import _lib, training_utils
     env_a = training_utils.load_model_and_create_env("", helpers.env_config(), model=model)
     env_b = training_utils.load_model_and_create_env("", helpers.env_config(), model=model, flags=_lib.FLAG_NO_SPEC_RESET)
     assert env_b[9].sys.lib.mjxb_model_flags(env_b[9].sys.handle) & _lib.FLAG_NO_SPEC_RESET
     assert env_a[9].sys.lib.mjxb_model_flags(env_a[9].sys.handle) & _lib.FLAG_NO_SPEC_RESET == 0
-    for n in (1, 37, 1024, 1184, 1185):
+    # (<= 2072 envs: one round of stepping + reset warps; up to 8288 envs: two to four such rounds; forced resets exceed the reset
+    #  warps of some CTAs; 8300 envs: five rounds, deferred resets in both models)
+    for n in (1, 37, 1024, 1184, 1185, 2048, 2072, 2073, 4100, 8288, 8300):
         keys = helpers.ppo_keys(n, n)
         sa, oa = env_a[8](keys)
         sb, ob = env_b[8](keys)
