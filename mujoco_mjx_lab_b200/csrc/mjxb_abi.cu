@@ -66,6 +66,7 @@ struct Tuning {
   bool host_direct = true, direct_obs = true, direct_scalars = true;
   int host_chunks = 0;
   bool balance_rounds = true;
+  bool skip_mid = true;      // latency regime: the big tier consumes the main tier's overflow list directly; MJXB_SKIP_MID=0 keeps three tiers
   int spec_max_rounds = 4;   // concurrent auto-reset (reset warps beside the stepping warps) for batches of up to this many rounds; MJXB_SPEC_MAX_ROUNDS
   int sort_min_env = 16384;  // work-sorted scheduling from this batch size on (0 = never); MJXB_SORT_MIN_ENV
   int sort_seg_shift = 15;   // segment = 2^shift envs (one sort CTA each); the host pipeline uses its input-chunk size instead
@@ -259,13 +260,19 @@ int launch(const mjxb_model* m, const StepArgs& args_in, bool dbg, cudaStream_t 
   if (single) launch_pdl(mjxb_step_kernel<false, CAP_MAIN, MAXCC_MAIN, WARPS_MAIN, true, true>, dim3(grid), dim3(warps * 32), smem_main, stream,
                          (const DevModel*)m->dev, (const PairParam*)m->dev_pp, args);
   else MJXB_LAUNCH(CAP_MAIN, MAXCC_MAIN, WARPS_MAIN, grid, warps * 32, smem_main);
-  g_mjxb_launches += 3 + extra_launches;   // (the schedule sort) + main tier + the two overflow tiers below (each leaves at once when its list is empty)
+  // Every kernel boundary of a step costs ~6 us at small batches (14 us at 4096 envs), also for an overflow tier that finds its list empty
+  // and leaves at once (measured by skipping them: 1024 envs 81 -> 69 us per step). The latency regime (concurrent-reset launches,
+  // <= 8288 envs with auto-reset) therefore runs ONE overflow tier: the big one consumes the main tier's list directly. It holds every
+  // row of the model, so results are the same; what is given up is the mid tier's higher throughput (10 instead of 3 warps per SM)
+  // when many envs overflow, which an auto-resetting batch of that size does not have (5e-6 of the env-steps in the bench distribution).
+  const bool skip_mid = args.spec_reset != 0 && m->tune.skip_mid;
+  g_mjxb_launches += (skip_mid ? 2 : 3) + extra_launches;   // (the schedule sort) + main tier + the overflow tiers below (each leaves at once when its list is empty)
   cudaError_t e = cudaGetLastError();
   const bool sync_tiers = m->tune.sync_tiers;  // debugging aid: attribute a device fault to its tier
   if (sync_tiers && e == cudaSuccess) { e = cudaStreamSynchronize(stream); if (e != cudaSuccess) fprintf(stderr, "[mjxb] main tier failed: %s\n", cudaGetErrorString(e)); }
   args.in_ready = nullptr;  // only the first pass waits for streamed inputs
   args.perm = nullptr;      // (the overflow tiers read their own lists; they still leave cost keys)
-  if (e == cudaSuccess) {  // mid tier (64 rows / 24 contacts) over the envs the main tile could not hold; usually few: exits at once when empty
+  if (e == cudaSuccess && !skip_mid) {  // mid tier (64 rows / 24 contacts) over the envs the main tile could not hold; usually few: exits at once when empty
     args.in_count = ovf; args.in_done = ovf + 1; args.in_list = listA; args.out_count = ovf + 2; args.out_list = listB;
     const int wm = m->warps_mid;
     int gridm = m->num_sms;
@@ -277,6 +284,7 @@ int launch(const mjxb_model* m, const StepArgs& args_in, bool dbg, cudaStream_t 
   }
   if (e == cudaSuccess) {  // big tier: holds every static row / contact slot of the model
     args.in_count = ovf + 2; args.in_done = ovf + 3; args.in_list = listB; args.out_count = nullptr; args.out_list = nullptr;
+    if (skip_mid) { args.in_count = ovf; args.in_done = ovf + 1; args.in_list = listA; }
     const int wb = m->warps_big;
     int gridb = m->num_sms;
     if (gridb * wb > args.n_env) gridb = (args.n_env + wb - 1) / wb;
@@ -378,6 +386,7 @@ int mjxb_model_create_ex(const void* blob, size_t blob_bytes, const mjxb_env_con
   m->tune.sort_seg_shift = env_int("MJXB_SORT_SEG_SHIFT", m->tune.sort_seg_shift);
   m->tune.balance_rounds = env_int("MJXB_BALANCE_ROUNDS", 1) != 0;
   m->tune.spec_max_rounds = env_int("MJXB_SPEC_MAX_ROUNDS", m->tune.spec_max_rounds);
+  m->tune.skip_mid = env_int("MJXB_SKIP_MID", 1) != 0;
   m->tune.host_direct = env_int("MJXB_HOST_DIRECT", 1) != 0;
   m->tune.direct_obs = env_int("MJXB_DIRECT_OBS", 1) != 0;
   m->tune.direct_scalars = env_int("MJXB_DIRECT_SCALARS", 1) != 0;

@@ -60,3 +60,46 @@ def test_more_than_32_candidate_contacts(model, oracle):
     s = out["sensordata"].double().cpu().numpy()
     assert_f32_equivalent(rel(s, ref["sensordata"]).max(axis=1), rel(r32["sensordata"], ref["sensordata"]).max(axis=1), 1e-4,
                           "touch sensors of crumpled envs")
+
+
+def test_single_overflow_tier_in_the_latency_regime(model):
+    """Auto-resetting batches of up to four rounds run ONE overflow tier (the big one consumes the main tier's list directly: every kernel
+    boundary costs ~6 us there, mjxb_abi.cu launch()). Tumbling states that do overflow the 32-row tile -- some beyond the mid tier's 64
+    rows -- must come out bit-identical to the three-tier chain (MJXB_SKIP_MID=0 at model creation), over steps with resets."""
+    import os
+    from mujoco_mjx_lab_b200 import training_utils
+    env_a = training_utils.load_model_and_create_env("", helpers.env_config(), model=model)
+    os.environ["MJXB_SKIP_MID"] = "0"
+    try:
+        env_b = training_utils.load_model_and_create_env("", helpers.env_config(), model=model)
+    finally:
+        del os.environ["MJXB_SKIP_MID"]
+    n = 512
+    q, v, w, c = helpers.make_states(model, n, 77, "tumble")
+    t = lambda a: torch.tensor(a, dtype=torch.float32, device="cuda")
+    keys = helpers.ppo_keys(4, n)
+    outs = []
+    for env in (env_a, env_b):
+        (d, aux), _ = env[8](keys)
+        d.qpos.copy_(t(q)); d.qvel.copy_(t(v)); d.qacc_warmstart.copy_(t(w))
+        state = (d, aux)
+        status = torch.zeros(n, dtype=torch.int32, device="cuda")
+        launches0 = env[9].sys.lib.mjxb_launch_count()
+        rec = []
+        for step in range(4):
+            act = t(c) * (0.5 + 0.5 * step)
+            state, obs, r, te, tr = env[9].autoreset(state, act, helpers.ppo_keys(50 + step, n))
+            rec.append((obs.clone(), r.clone(), te.clone(), tr.clone(), state[0].qpos.clone(), state[0].qvel.clone(), state[1].clone()))
+        outs.append((rec, env[9].sys.lib.mjxb_launch_count() - launches0))
+    (ra, la), (rb, lb) = outs
+    assert la == 4 * 2 and lb == 4 * 3                                   # main + big   against   main + mid + big
+    for sa, sb in zip(ra, rb):
+        for xa, xb in zip(sa, sb):
+            assert torch.equal(xa, xb)
+    assert float(torch.stack([s[2] for s in ra]).sum()) > 0             # episodes did end (resets inside the overflow tier as well)
+    ref = helpers.make_oracle(model, helpers.env_config()) if False else None
+    # the states do overflow: the forward pass reports the row spill for a good part of the batch, some beyond 64 rows
+    sysm = mjx.put_model(model)
+    _, dbg = mjx.forward(sysm, mjx.Data(t(q), t(v), t(w), torch.zeros(n, device="cuda"), t(c)), debug=True)
+    ncand = (dbg["efc_active"] & 1).sum(1)
+    assert int((ncand > 32).sum()) >= 3 and int((ncand > 64).sum()) >= 1
