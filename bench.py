@@ -281,7 +281,7 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     traffic = None                                                # dram bytes per step launch from the committed ncu capture
     try:
-        tp = [q for q in (os.path.join(ROOT, "profiles", f) for f in ("r2c_traffic.json", "r2_traffic.json", "r1_traffic.json")) if os.path.exists(q)]
+        tp = [q for q in (os.path.join(ROOT, "profiles", f) for f in ("r2d_traffic.json", "r2_traffic.json", "r1_traffic.json")) if os.path.exists(q)]
         tj = json.load(open(tp[0]))
         if int(tj["n_env"]) == n:
             traffic = float(tj["dram_bytes_per_launch"])
