@@ -246,12 +246,13 @@ def main():
     ffma_tf, ffma_ms = C.c_float(0), C.c_float(0)
     _lib.check(L.mjxb_ffma_peak(local_rank, C.byref(ffma_tf), C.byref(ffma_ms)), "mjxb_ffma_peak")
 
-    # ---- BASELINE configs[0..1]: the small batches the reference itself runs (64 = its CPU case, 4096 = mjx_humanoid_speed_test.py:141,
-    # 1024 = its PPO batch), both input distributions of SURVEY.md 8d, on this rank's GPU
+    # ---- BASELINE configs[0..1]: the batch sizes the reference itself runs (64 = its CPU case, 4096 = mjx_humanoid_speed_test.py:141,
+    # 1024 / 2048 = its PPO batches) and the rest of the 1K-256K sweep of configs[1] (the headline above is its 262,144-env point), both
+    # input distributions of SURVEY.md 8d, on this rank's GPU
     sweep = []
     if not args.no_sweep:
         del state, obs
-        for ns in (64, 1024, 4096):
+        for ns in (64, 1024, 2048, 4096, 16384, 65536):
             sweep.append(sweep_point(ns, v_reset, v_step, env_sys, nu, dev))
 
     # ---- PPO iteration time (the second half of BASELINE.json's metric): the caller of the hot path, reference train_ppo.py
