@@ -161,8 +161,9 @@ def test_fused_learner_equals_torch_learner(env):
     # function computed is the unpadded network's
     od, nu = a.sys.obs_dim, a.sys.nu
     assert a.kpad == 64 and a._pol_pad[0].shape == (64, 256) and a._pol_pad[-2].shape == (256, 32)
-    assert float(a._pol_pad[0][od:].abs().max()) == 0.0 and float(a._val_pad[0][od:].abs().max()) == 0.0
-    assert float(a._pol_pad[-2][:, nu:].abs().max()) == 0.0 and float(a._pol_pad[-1][nu:].abs().max()) == 0.0
+    with torch.no_grad():
+        assert float(a._pol_pad[0][od:].abs().max()) == 0.0 and float(a._val_pad[0][od:].abs().max()) == 0.0
+        assert float(a._pol_pad[-2][:, nu:].abs().max()) == 0.0 and float(a._pol_pad[-1][nu:].abs().max()) == 0.0
     assert all(p.data_ptr() % 256 == 0 for p in a._pol_pad + [a.log_std] + a._val_pad)
     used = sum(p.numel() for p in a._pol_pad + [a.log_std] + a._val_pad)
     mask = torch.ones_like(a.flat_p, dtype=torch.bool)
