@@ -69,7 +69,8 @@ struct Tuning {
   bool skip_mid = true;      // latency regime: the big tier consumes the main tier's overflow list directly; MJXB_SKIP_MID=0 keeps three tiers
   int spec_max_rounds = 4;   // concurrent auto-reset (reset warps beside the stepping warps) for batches of up to this many rounds; MJXB_SPEC_MAX_ROUNDS
   int sort_min_env = 16384;  // work-sorted scheduling from this batch size on (0 = never); MJXB_SORT_MIN_ENV
-  int sort_seg_shift = 15;   // segment = 2^shift envs (one sort CTA each); the host pipeline uses its input-chunk size instead
+  int sort_seg_shift = 11;   // segment = 2^shift envs (one sort CTA each: 128 CTAs at 262,144 envs; 2^15-env segments cost 2-3 % at 65,536 envs:
+                             // the sort's own latency); never larger than an input chunk of the host pipeline
 };
 
 // Per-stream launch scratch (overflow counters + lists + per-CTA reset queues). One entry per stream that has launched on the model, so
@@ -240,7 +241,8 @@ int launch(const mjxb_model* m, const StepArgs& args_in, bool dbg, cudaStream_t 
   if (m->tune.sort_min_env > 0 && args.n_env >= m->tune.sort_min_env && (args.mode == MODE_ENV_STEP || args.mode == MODE_PHYS_STEP) && !dbg) {
     int* perm = ovf + m->sched_offset(cap);
     uint8_t* work = reinterpret_cast<uint8_t*>(perm + cap);
-    const int shift = args.in_ready != nullptr ? args.in_ready_shift : m->tune.sort_seg_shift;  // streamed inputs: never reorder across chunks
+    int shift = m->tune.sort_seg_shift;
+    if (args.in_ready != nullptr && args.in_ready_shift < shift) shift = args.in_ready_shift;   // streamed inputs: never reorder across chunks
     launch_pdl(mjxb_sort_work_kernel, dim3((args.n_env + (1 << shift) - 1) >> shift), dim3(1024), 0, stream, (const uint8_t*)work, perm, args.n_env, shift);
     args.perm = perm; args.work_out = work;
     extra_launches = 1;
