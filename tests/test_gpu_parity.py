@@ -287,13 +287,13 @@ def test_host_buffer_api(model, env):
     assert L.mjxb_step_host(h, n + 1, act.ctypes.data, obs_h.ctypes.data, r_h.ctypes.data, te_h.ctypes.data, tr_h.ctypes.data) == -1
 
 
-def test_host_buffer_api_pinned_direct(model, env):
+@pytest.mark.parametrize("n", [20000, 5000])              # 5 input chunks of 4096 envs (work-sorted, deferred resets) / 2 chunks, reset warps
+def test_host_buffer_api_pinned_direct(model, env, n):
     """Pinned caller buffers take the direct pipeline (one launch, inputs behind per-chunk ready flags, obs stored straight into the
     caller's mapped buffer): same bits as the device-pointer API, over several input chunks and several calls (flag epochs)."""
     from mujoco_mjx_lab_b200 import _lib
     v_reset, v_step = env[8], env[9]
     L, h = _lib.lib(), v_step.sys.handle
-    n = 20000                                                  # 5 input chunks of 4096 envs
     keys = helpers.ppo_keys(9, n)
     pin = lambda *shape, dt=torch.float32: torch.zeros(*shape, dtype=dt).pin_memory()
     obs_h, r_h, te_h, tr_h, act_h = pin(n, 54), pin(n), pin(n), pin(n), pin(n, 21)
