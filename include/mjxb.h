@@ -118,7 +118,7 @@ int mjxb_model_create(const void* blob, size_t blob_bytes, const mjxb_env_config
                                       select the closed-form exact minimiser */
 #define MJXB_FLAG_DENSE_CHOL 2u    /* dense right-looking Cholesky instead of the generated tree-ordered elimination */
 #define MJXB_FLAG_INLINE_RESET 4u  /* auto-reset runs inline instead of in deferred packed rounds */
-#define MJXB_FLAG_NO_SPEC_RESET 8u /* never run the auto-reset on reset warps beside the step rounds (batches of up to four rounds, <= 8288 envs):
+#define MJXB_FLAG_NO_SPEC_RESET 8u /* never run the auto-reset on reset warps beside the step rounds (batches of up to six rounds, <= 12,432 envs):
                                       always the deferred packed reset rounds after the step rounds */
 #define MJXB_FLAG_NO_WORK_SORT 16u /* never deal the envs of a large batch (>= 16,384) to the CTAs in order of their previous step's Newton
                                       iteration count (the work-sorted schedule: one extra small launch per step, identical results) */

@@ -67,7 +67,7 @@ struct Tuning {
   int host_chunks = 0;
   bool balance_rounds = true;
   bool skip_mid = true;      // latency regime: the big tier consumes the main tier's overflow list directly; MJXB_SKIP_MID=0 keeps three tiers
-  int spec_max_rounds = 4;   // concurrent auto-reset (reset warps beside the stepping warps) for batches of up to this many rounds; MJXB_SPEC_MAX_ROUNDS
+  int spec_max_rounds = 6;   // concurrent auto-reset (reset warps beside the stepping warps) for batches of up to this many rounds; MJXB_SPEC_MAX_ROUNDS
   int sort_min_env = 16384;  // work-sorted scheduling from this batch size on (0 = never); MJXB_SORT_MIN_ENV
   int sort_seg_shift = 11;   // segment = 2^shift envs (one sort CTA each: 128 CTAs at 262,144 envs; 2^15-env segments cost 2-3 % at 65,536 envs:
                              // the sort's own latency); never larger than an input chunk of the host pipeline
@@ -217,8 +217,8 @@ int launch(const mjxb_model* m, const StepArgs& args_in, bool dbg, cudaStream_t 
   const bool single_ = !dbg && ls_ && args.nsteps == 1 && (!(args.mode == MODE_ENV_STEP && args.autoreset) || args.reset_list != nullptr);
   // concurrent auto-reset for batches of a few rounds: `steppers` stepping warps + reset warps per CTA; an env that finishes its episode
   // is re-initialised by a reset warp beside the step round instead of in a packed pass after the step rounds (bit-identical results;
-  // 1024 envs: 105.6 -> 81 us per step, 2048 envs: 142 -> 106 us, 4096 envs 21.5 -> 26.0 M env-steps/s, 8192 envs 25.1 -> 27.7 M). From
-  // five rounds on (16,384 envs: 29.5 against 28.4 M) all 16 warps step and the resets run in packed rounds at the end (2 rounds in
+  // 1024 envs: 105.6 -> 81 us per step, 2048 envs: 142 -> 106 us, 4096 envs 21.5 -> 26.0 M env-steps/s, 8192 envs 25.1 -> 27.7 M). 10,240 / 12,288 envs
+  // (5 / 6 rounds) +7 / +5 %. From seven rounds on (14,000 envs: 29.4 against 28.4 M) all 16 warps step and the resets run in packed rounds at the end (2 rounds in
   // 113 at 262,144 envs).
   args.spec_reset = 0;
   if (m->tune.spec_reset && single_ && args.mode == MODE_ENV_STEP && args.autoreset) {
@@ -264,7 +264,7 @@ int launch(const mjxb_model* m, const StepArgs& args_in, bool dbg, cudaStream_t 
   else MJXB_LAUNCH(CAP_MAIN, MAXCC_MAIN, WARPS_MAIN, grid, warps * 32, smem_main);
   // Every kernel boundary of a step costs ~6 us at small batches (14 us at 4096 envs), also for an overflow tier that finds its list empty
   // and leaves at once (measured by skipping them: 1024 envs 81 -> 69 us per step). The latency regime (concurrent-reset launches,
-  // <= 8288 envs with auto-reset) therefore runs ONE overflow tier: the big one consumes the main tier's list directly. It holds every
+  // <= 12,432 envs with auto-reset) therefore runs ONE overflow tier: the big one consumes the main tier's list directly. It holds every
   // row of the model, so results are the same; what is given up is the mid tier's higher throughput (10 instead of 3 warps per SM)
   // when many envs overflow, which an auto-resetting batch of that size does not have (5e-6 of the env-steps in the bench distribution).
   const bool skip_mid = args.spec_reset != 0 && m->tune.skip_mid;

@@ -63,7 +63,7 @@ def test_more_than_32_candidate_contacts(model, oracle):
 
 
 def test_single_overflow_tier_in_the_latency_regime(model):
-    """Auto-resetting batches of up to four rounds run ONE overflow tier (the big one consumes the main tier's list directly: every kernel
+    """Auto-resetting batches of up to six rounds run ONE overflow tier (the big one consumes the main tier's list directly: every kernel
     boundary costs ~6 us there, mjxb_abi.cu launch()). Tumbling states that do overflow the 32-row tile -- some beyond the mid tier's 64
     rows -- must come out bit-identical to the three-tier chain (MJXB_SKIP_MID=0 at model creation), over steps with resets."""
     import os

@@ -64,9 +64,9 @@ def test_speculative_reset_is_bit_identical(model):
     env_b = training_utils.load_model_and_create_env("", helpers.env_config(), model=model, flags=_lib.FLAG_NO_SPEC_RESET)
     assert env_b[9].sys.lib.mjxb_model_flags(env_b[9].sys.handle) & _lib.FLAG_NO_SPEC_RESET
     assert env_a[9].sys.lib.mjxb_model_flags(env_a[9].sys.handle) & _lib.FLAG_NO_SPEC_RESET == 0
-    # (<= 2072 envs: one round of stepping + reset warps; up to 8288 envs: two to four such rounds; forced resets exceed the reset
-    #  warps of some CTAs; 8300 envs: five rounds, deferred resets in both models)
-    for n in (1, 37, 1024, 1184, 1185, 2048, 2072, 2073, 4100, 8288, 8300):
+    # (<= 2072 envs: one round of stepping + reset warps; up to 12,432 envs: two to six such rounds; forced resets exceed the reset
+    #  warps of some CTAs; 12,500 envs: seven rounds, deferred resets in both models)
+    for n in (1, 37, 1024, 1184, 1185, 2048, 2072, 2073, 4100, 8288, 12432, 12500):
         keys = helpers.ppo_keys(n, n)
         sa, oa = env_a[8](keys)
         sb, ob = env_b[8](keys)
