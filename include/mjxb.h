@@ -122,6 +122,8 @@ int mjxb_model_create(const void* blob, size_t blob_bytes, const mjxb_env_config
                                       always the deferred packed reset rounds after the step rounds */
 #define MJXB_FLAG_NO_WORK_SORT 16u /* never deal the envs of a large batch (>= 16,384) to the CTAs in order of their previous step's Newton
                                       iteration count (the work-sorted schedule: one extra small launch per step, identical results) */
+#define MJXB_FLAG_NO_DYN_ROUNDS 32u /* static (round, CTA) assignment of the env groups instead of a device-wide group counter (batches of
+                                      several rounds per SM; identical results) */
 #define MJXB_FLAG_BUILD_EXACT 256u /* (reported only) the library is the reference-arithmetic build: no fast-math, no FMA contraction */
 int mjxb_model_create_ex(const void* blob, size_t blob_bytes, const mjxb_env_config* cfg, int device, uint32_t flags,
                          mjxb_model** out);

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("MJXB_LIB", os.path.join(_HERE, "libmjxb.so"))  # MJXB
 # the reference-arithmetic build of the same sources (no fast-math, no FMA contraction, MJX's iterative line search): the yardstick the
 # parity tests measure the product against (csrc/Makefile); never a fallback
 EXACT_LIB_PATH = os.path.join(_HERE, "libmjxb_exact.so")
-FLAG_LS_ITERATIVE, FLAG_DENSE_CHOL, FLAG_INLINE_RESET, FLAG_NO_SPEC_RESET, FLAG_NO_WORK_SORT, FLAG_BUILD_EXACT = 1, 2, 4, 8, 16, 256
+FLAG_LS_ITERATIVE, FLAG_DENSE_CHOL, FLAG_INLINE_RESET, FLAG_NO_SPEC_RESET, FLAG_NO_WORK_SORT, FLAG_NO_DYN_ROUNDS, FLAG_BUILD_EXACT = 1, 2, 4, 8, 16, 32, 256
 
 ERRORS = {0: "ok", -1: "invalid argument", -2: "bad model blob", -3: "CUDA error", -4: "no CUDA device (no CPU fallback)",
           -5: "unsupported model"}

@@ -66,6 +66,7 @@ struct Tuning {
   bool host_direct = true, direct_obs = true, direct_scalars = true;
   int host_chunks = 0;
   bool balance_rounds = true;
+  bool dyn_rounds = true;    // groups of envs taken from a device-wide counter (batches of >= 2 rounds per CTA without reset warps); MJXB_DYN_ROUNDS
   bool skip_mid = true;      // latency regime: the big tier consumes the main tier's overflow list directly; MJXB_SKIP_MID=0 keeps three tiers
   int spec_max_rounds = 6;   // concurrent auto-reset (reset warps beside the stepping warps) for batches of up to this many rounds; MJXB_SPEC_MAX_ROUNDS
   int sort_min_env = 16384;  // work-sorted scheduling from this batch size on (0 = never); MJXB_SORT_MIN_ENV
@@ -95,7 +96,9 @@ struct mjxb_model {
   mutable std::vector<int*> scratch_retired; // superseded buffers (freed at destroy)
   Arena arena;
   size_t sched_offset(int n_env) const { return 3 * (size_t)n_env + 4 + (size_t)num_sms * kMaxWarps * 2; }   // ints before perm
-  size_t scratch_ints(int n_env) const { return sched_offset(n_env) + (size_t)n_env + ((size_t)n_env + 3) / 4; }
+  size_t dyn_offset(int n_env) const { return sched_offset(n_env) + (size_t)n_env + ((size_t)n_env + 3) / 4; }   // ints before the group counter
+  // ... then 4 counter ints and the reset queues of the dynamic rounds (twice as deep as the static ones: a CTA may take up to twice its share)
+  size_t scratch_ints(int n_env) const { return dyn_offset(n_env) + 4 + 2 * (size_t)n_env + (size_t)num_sms * kMaxWarps * 4; }
 };
 
 namespace {
@@ -145,6 +148,7 @@ int arena_ensure(mjxb_model* m, int n) {
     CU(cudaMalloc(&a.pipe_ovf[i], m->scratch_ints(a.chunk) * sizeof(int)));
     CU(cudaMemsetAsync(a.pipe_ovf[i], 0, 4 * sizeof(int), a.stream));
     CU(cudaMemsetAsync(a.pipe_ovf[i] + m->sched_offset(a.chunk) + a.chunk, 0, (size_t)a.chunk, a.stream));
+    CU(cudaMemsetAsync(a.pipe_ovf[i] + m->dyn_offset(a.chunk), 0, 4 * sizeof(int), a.stream));
   }
   CU(cudaMalloc(&a.ready, Arena::kReadyMax * sizeof(unsigned)));
   CU(cudaMemsetAsync(a.ready, 0, Arena::kReadyMax * sizeof(unsigned), a.stream));
@@ -177,6 +181,7 @@ int scratch_for(const mjxb_model* m, cudaStream_t stream, int n_env, int** buf, 
   CU(cudaMalloc(&nb, m->scratch_ints(n_env) * sizeof(int)));
   CU(cudaMemsetAsync(nb, 0, 4 * sizeof(int), stream));
   CU(cudaMemsetAsync(nb + m->sched_offset(n_env) + n_env, 0, (size_t)n_env, stream));   // cost keys: no hint yet
+  CU(cudaMemsetAsync(nb + m->dyn_offset(n_env), 0, 4 * sizeof(int), stream));           // group counter of the dynamic rounds
   if (s == nullptr) { m->scratch.push_back(Scratch()); s = &m->scratch.back(); s->stream = stream; }
   else m->scratch_retired.push_back(s->buf);  // earlier launches / captured graphs may still reference it
   s->buf = nb; s->cap = n_env;
@@ -249,6 +254,18 @@ int launch(const mjxb_model* m, const StepArgs& args_in, bool dbg, cudaStream_t 
   }
   const size_t smem_main = m->smem - (size_t)(m->warps - warps) * sizeof(WarpS<CAP_MAIN, MAXCC_MAIN>);
   args.reset_stride = ((args.n_env + grid * warps - 1) / (grid * warps)) * warps;
+  // dynamic rounds: from two rounds per CTA on (and no reset warps), groups of envs are taken from a device-wide counter
+  args.dyn_counter = nullptr; args.dyn_done = nullptr; args.dyn_max_rounds = 0;
+  {
+    const int rounds = (args.n_env + grid * warps - 1) / (grid * warps);
+    if (m->tune.dyn_rounds && single_ && args.spec_reset == 0 && rounds >= 2 && (args.mode == MODE_ENV_STEP || args.mode == MODE_PHYS_STEP) && !dbg) {
+      int* dynp = ovf + m->dyn_offset(cap);
+      args.dyn_counter = dynp; args.dyn_done = dynp + 1;
+      args.dyn_max_rounds = 2 * rounds;                       // grid * 2 * rounds * warps <= 2 * (n_env + grid * warps) queue slots
+      args.reset_stride = args.dyn_max_rounds * warps;
+      if (args.reset_list != nullptr) args.reset_list = dynp + 4;
+    }
+  }
   const bool ls = m->host.ls_exact != 0 && m->host.solver == 2;  // fast instantiation: Newton + exact line search; else the general one
 #define MJXB_LAUNCH(CAPv, CCv, Wv, G, B, SM)                                                                                   \
   do {                                                                                                                        \
@@ -259,7 +276,10 @@ int launch(const mjxb_model* m, const StepArgs& args_in, bool dbg, cudaStream_t 
   } while (0)
   // hot instantiation: one step per launch, Newton + exact line search, resets deferred (or none requested)
   const bool single = !dbg && ls && args.nsteps == 1 && (!(args.mode == MODE_ENV_STEP && args.autoreset) || args.reset_list != nullptr);
-  if (single) launch_pdl(mjxb_step_kernel<false, CAP_MAIN, MAXCC_MAIN, WARPS_MAIN, true, true>, dim3(grid), dim3(warps * 32), smem_main, stream,
+  if (single && args.dyn_counter != nullptr)
+    launch_pdl(mjxb_step_kernel<false, CAP_MAIN, MAXCC_MAIN, WARPS_MAIN, true, true, true>, dim3(grid), dim3(warps * 32), smem_main, stream,
+               (const DevModel*)m->dev, (const PairParam*)m->dev_pp, args);
+  else if (single) launch_pdl(mjxb_step_kernel<false, CAP_MAIN, MAXCC_MAIN, WARPS_MAIN, true, true>, dim3(grid), dim3(warps * 32), smem_main, stream,
                          (const DevModel*)m->dev, (const PairParam*)m->dev_pp, args);
   else MJXB_LAUNCH(CAP_MAIN, MAXCC_MAIN, WARPS_MAIN, grid, warps * 32, smem_main);
   // Every kernel boundary of a step costs ~6 us at small batches (14 us at 4096 envs), also for an overflow tier that finds its list empty
@@ -274,6 +294,7 @@ int launch(const mjxb_model* m, const StepArgs& args_in, bool dbg, cudaStream_t 
   if (sync_tiers && e == cudaSuccess) { e = cudaStreamSynchronize(stream); if (e != cudaSuccess) fprintf(stderr, "[mjxb] main tier failed: %s\n", cudaGetErrorString(e)); }
   args.in_ready = nullptr;  // only the first pass waits for streamed inputs
   args.perm = nullptr;      // (the overflow tiers read their own lists; they still leave cost keys)
+  args.dyn_counter = nullptr; args.dyn_done = nullptr;
   if (e == cudaSuccess && !skip_mid) {  // mid tier (64 rows / 24 contacts) over the envs the main tile could not hold; usually few: exits at once when empty
     args.in_count = ovf; args.in_done = ovf + 1; args.in_list = listA; args.out_count = ovf + 2; args.out_list = listB;
     const int wm = m->warps_mid;
@@ -387,6 +408,7 @@ int mjxb_model_create_ex(const void* blob, size_t blob_bytes, const mjxb_env_con
   m->tune.sort_min_env = (flags & MJXB_FLAG_NO_WORK_SORT) ? 0 : env_int("MJXB_SORT_MIN_ENV", m->tune.sort_min_env);
   m->tune.sort_seg_shift = env_int("MJXB_SORT_SEG_SHIFT", m->tune.sort_seg_shift);
   m->tune.balance_rounds = env_int("MJXB_BALANCE_ROUNDS", 1) != 0;
+  m->tune.dyn_rounds = env_int("MJXB_DYN_ROUNDS", 1) != 0 && !(flags & MJXB_FLAG_NO_DYN_ROUNDS);
   m->tune.spec_max_rounds = env_int("MJXB_SPEC_MAX_ROUNDS", m->tune.spec_max_rounds);
   m->tune.skip_mid = env_int("MJXB_SKIP_MID", 1) != 0;
   m->tune.host_direct = env_int("MJXB_HOST_DIRECT", 1) != 0;
@@ -422,6 +444,7 @@ int mjxb_model_create_ex(const void* blob, size_t blob_bytes, const mjxb_env_con
   CUX(cudaFuncSetAttribute(mjxb_step_kernel<DBGv, CAP_BIG, MAXCC_BIG, WARPS_BIG, LSv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem_big));
   MJXB_SMEM_ATTR(false, true) MJXB_SMEM_ATTR(true, true) MJXB_SMEM_ATTR(false, false) MJXB_SMEM_ATTR(true, false)
   CUX(cudaFuncSetAttribute(mjxb_step_kernel<false, CAP_MAIN, MAXCC_MAIN, WARPS_MAIN, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem));
+  CUX(cudaFuncSetAttribute(mjxb_step_kernel<false, CAP_MAIN, MAXCC_MAIN, WARPS_MAIN, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->smem));
 #undef MJXB_SMEM_ATTR
   CUX(cudaMalloc(&m->dev, sizeof(DevModel)));
   CUX(cudaMalloc(&m->dev_pp, sizeof(pp)));
@@ -479,6 +502,7 @@ int mjxb_model_flags(const mjxb_model* m) {
   if (m->tune.inline_reset) f |= MJXB_FLAG_INLINE_RESET;
   if (!m->tune.spec_reset) f |= MJXB_FLAG_NO_SPEC_RESET;
   if (m->tune.sort_min_env <= 0) f |= MJXB_FLAG_NO_WORK_SORT;
+  if (!m->tune.dyn_rounds) f |= MJXB_FLAG_NO_DYN_ROUNDS;
 #if MJXB_EXACT
   f |= MJXB_FLAG_BUILD_EXACT;
 #endif

@@ -51,6 +51,11 @@ struct StepArgs {
   // runs in lockstep need about the same number of Newton iterations; every env leaves its cost key (this step's iteration count) in
   // `work_out` for the next launch on the stream. A stale or missing hint only costs time: results do not depend on the order.
   const int* perm; uint8_t* work_out;
+  // dynamic rounds (batches of several rounds without reset warps): a CTA takes its next group of envs from a device-wide counter when it
+  // has finished a round, instead of the static (round, CTA) assignment -- CTAs whose rounds ran long take fewer of them. dyn_counter /
+  // dyn_done live in the stream's scratch (zero between launches: the last CTA out resets them); a CTA takes at most dyn_max_rounds
+  // groups (the capacity of its reset queue).
+  int* dyn_counter; int* dyn_done; int dyn_max_rounds;
   int lockstep;          // CTA barriers keep the warps of an SM in the same code region (instruction-cache locality)
   int lockstep_group;    // warps per barrier group (0 = the whole CTA)
   // host-buffer pipeline: action / keys arrive in chunks of (1 << in_ready_shift) envs while the kernel already runs; the copy
@@ -533,7 +538,8 @@ __global__ void __launch_bounds__(1024) mjxb_sort_work_kernel(const uint8_t* __r
 #define MJXB_FOR_ROW_STRIPS(r) _Pragma("unroll") for (int r = lane, strip_ = 0; strip_ < NSTRIP && r < nrow; strip_++, r += 32)
 // ------------------------------------------------------------------------------------------- the kernel
 // SINGLE: one step per launch and resets always deferred -> no loop-carried per-env registers across the step / pass loops.
-template <bool DBG, int CAP, int MAXCC, int MAXW, bool LS_EXACT, bool SINGLE = false>
+// DYN: groups of envs are taken from a device-wide counter (StepArgs::dyn_counter) instead of the static (round, CTA) assignment.
+template <bool DBG, int CAP, int MAXCC, int MAXW, bool LS_EXACT, bool SINGLE = false, bool DYN = false>
 __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel* __restrict__ gmodel, const PairParam* __restrict__ pair_param,
                                                             StepArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -558,6 +564,7 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
   __shared__ int s_spec_need[32];   // per stepping slot: 0 = the env goes on, 1 = it finishes and a reset warp serves it, 2 = finishes, unserved
   __shared__ int s_need_slot[32];   // the slots that need a reset, in order of publication
   __shared__ int s_pub_count, s_need_count;
+  __shared__ int s_dyn_base;
   if (threadIdx.x == 0) { s_reset_count = 0; s_pub_count = 0; s_need_count = 0; }
   if (threadIdx.x < 32) s_spec_need[threadIdx.x] = 0;
   __syncthreads();
@@ -578,14 +585,21 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
   const bool spec_warp = spec && warp >= nslot;            // this warp is a reset warp of the step round
   const int n_rounds = (n_items + gridDim.x * nslot - 1) / (gridDim.x * nslot);
   const bool defer = A.autoreset && A.reset_list != nullptr && A.mode == MODE_ENV_STEP;
-  int total_rounds = n_rounds, n_reset = 0;
+  constexpr bool dyn = DYN;                                // (the host launches this instantiation only without reset warps / input lists)
+  int total_rounds = n_rounds, n_reset = 0, reset_round0 = n_rounds;
   bool reset_phase = false;
   for (int round = 0;; round++) {
+    if (dyn && !reset_phase) {   // take the next group of envs
+      if (threadIdx.x == 0) s_dyn_base = round < A.dyn_max_rounds ? atomicAdd(A.dyn_counter, nslot) : n_items;
+      __syncthreads();
+      total_rounds = s_dyn_base < n_items ? round + 1 : round;
+    }
     if (round == total_rounds) {  // CTA-uniform: after the step rounds, the queued resets run 16 per round
       if (reset_phase || !defer) break;
       __syncthreads();
       n_reset = s_reset_count;
       reset_phase = true;
+      reset_round0 = round;
       total_rounds += (n_reset + nwarp - 1) / nwarp;
       if (round == total_rounds) break;
     }
@@ -621,11 +635,11 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
     if (!reset_phase) {
       // sorted schedule: odd rounds deal the groups to the CTAs in reverse, so that a CTA's heavy groups are paired with light ones
       const int cta = (A.perm != nullptr && (round & 1)) ? (int)gridDim.x - 1 - (int)blockIdx.x : (int)blockIdx.x;
-      const int item = (round * gridDim.x + cta) * nslot + wslot;
+      const int item = dyn ? s_dyn_base + wslot : (round * gridDim.x + cta) * nslot + wslot;
       valid = item < n_items;
       env = valid ? (consuming ? A.in_list[item] : (A.perm != nullptr ? A.perm[item] : item)) : (consuming ? A.in_list[0] : 0);
     } else {
-      const int idx = (round - n_rounds) * nwarp + warp;
+      const int idx = (round - reset_round0) * nwarp + warp;
       valid = idx < n_reset;
       env = A.reset_list[(size_t)blockIdx.x * A.reset_stride + (valid ? idx : 0)];
     }
@@ -1906,6 +1920,14 @@ __global__ void __launch_bounds__(MAXW * 32, 1) mjxb_step_kernel(const DevModel*
     if (A.status && lane == 0) A.status[env] = reset_phase ? (A.status[env] | status) : status;
     MJXB_STAMP(13);
     __syncwarp();
+  }
+  if (dyn) {  // last CTA out re-arms the group counter for the next launch
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const int t = atomicAdd(A.dyn_done, 1);
+      if (t == (int)gridDim.x - 1) { *A.dyn_counter = 0; *A.dyn_done = 0; __threadfence(); }
+    }
   }
   if (consuming) {  // last CTA out resets the consumed list's counters for the next step
     __syncthreads();

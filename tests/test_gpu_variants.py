@@ -87,14 +87,17 @@ def test_speculative_reset_is_bit_identical(model):
 
 
 def test_work_sorted_schedule_is_bit_identical(model):
-    """Large batches deal the envs to the CTAs by descending Newton-iteration count of their previous step (mjxb_abi.cu launch(),
-    mjxb_sort_work_kernel): the order in which envs are processed changes, no result does -- device API over steps that reset envs
+    """Large batches deal the envs to the CTAs by descending cost of their previous step (mjxb_abi.cu launch(), mjxb_sort_work_kernel)
+    and let a CTA take its next group of envs from a device-wide counter (dynamic rounds) instead of a static (round, CTA) assignment:
+    the order in which envs are processed changes, no result does -- device API over steps that reset envs
     (a batch size that is not a multiple of the sort segment), and the pinned host pipeline whose input chunks are the sort segments."""
     import helpers
     from mujoco_mjx_lab_b200 import _lib, training_utils
     env_a = training_utils.load_model_and_create_env("", helpers.env_config(), model=model)
-    env_b = training_utils.load_model_and_create_env("", helpers.env_config(), model=model, flags=_lib.FLAG_NO_WORK_SORT)
+    env_b = training_utils.load_model_and_create_env("", helpers.env_config(), model=model, flags=_lib.FLAG_NO_WORK_SORT | _lib.FLAG_NO_DYN_ROUNDS)
     assert env_b[9].sys.lib.mjxb_model_flags(env_b[9].sys.handle) & _lib.FLAG_NO_WORK_SORT
+    assert env_b[9].sys.lib.mjxb_model_flags(env_b[9].sys.handle) & _lib.FLAG_NO_DYN_ROUNDS
+    assert env_a[9].sys.lib.mjxb_model_flags(env_a[9].sys.handle) & _lib.FLAG_NO_DYN_ROUNDS == 0
     assert env_a[9].sys.lib.mjxb_model_flags(env_a[9].sys.handle) & _lib.FLAG_NO_WORK_SORT == 0
     n = 40000 + 123
     keys = helpers.ppo_keys(5, n)
