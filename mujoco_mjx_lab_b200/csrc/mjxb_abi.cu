@@ -66,6 +66,7 @@ struct Tuning {
   bool host_direct = true, direct_obs = true, direct_scalars = true;
   int host_chunks = 0;
   bool balance_rounds = true;
+  bool dyn_spec = true;      // ... also in the rounds that run reset warps; MJXB_DYN_SPEC
   bool dyn_rounds = true;    // groups of envs taken from a device-wide counter (batches of >= 2 rounds per CTA without reset warps); MJXB_DYN_ROUNDS
   bool skip_mid = true;      // latency regime: the big tier consumes the main tier's overflow list directly; MJXB_SKIP_MID=0 keeps three tiers
   int spec_max_rounds = 6;   // concurrent auto-reset (reset warps beside the stepping warps) for batches of up to this many rounds; MJXB_SPEC_MAX_ROUNDS
@@ -254,11 +255,13 @@ int launch(const mjxb_model* m, const StepArgs& args_in, bool dbg, cudaStream_t 
   }
   const size_t smem_main = m->smem - (size_t)(m->warps - warps) * sizeof(WarpS<CAP_MAIN, MAXCC_MAIN>);
   args.reset_stride = ((args.n_env + grid * warps - 1) / (grid * warps)) * warps;
-  // dynamic rounds: from two rounds per CTA on (and no reset warps), groups of envs are taken from a device-wide counter
+  // dynamic rounds: from two rounds per CTA on, groups of envs (one per stepping warp) are taken from a device-wide counter
   args.dyn_counter = nullptr; args.dyn_done = nullptr; args.dyn_max_rounds = 0;
   {
-    const int rounds = (args.n_env + grid * warps - 1) / (grid * warps);
-    if (m->tune.dyn_rounds && single_ && args.spec_reset == 0 && rounds >= 2 && (args.mode == MODE_ENV_STEP || args.mode == MODE_PHYS_STEP) && !dbg) {
+    const int per_round = grid * (args.spec_reset != 0 ? args.spec_reset : warps);
+    const int rounds = (args.n_env + per_round - 1) / per_round;
+    if (m->tune.dyn_rounds && single_ && (args.spec_reset == 0 || m->tune.dyn_spec) && rounds >= 2 &&
+        (args.mode == MODE_ENV_STEP || args.mode == MODE_PHYS_STEP) && !dbg) {
       int* dynp = ovf + m->dyn_offset(cap);
       args.dyn_counter = dynp; args.dyn_done = dynp + 1;
       args.dyn_max_rounds = 2 * rounds;                       // grid * 2 * rounds * warps <= 2 * (n_env + grid * warps) queue slots
@@ -409,6 +412,7 @@ int mjxb_model_create_ex(const void* blob, size_t blob_bytes, const mjxb_env_con
   m->tune.sort_seg_shift = env_int("MJXB_SORT_SEG_SHIFT", m->tune.sort_seg_shift);
   m->tune.balance_rounds = env_int("MJXB_BALANCE_ROUNDS", 1) != 0;
   m->tune.dyn_rounds = env_int("MJXB_DYN_ROUNDS", 1) != 0 && !(flags & MJXB_FLAG_NO_DYN_ROUNDS);
+  m->tune.dyn_spec = env_int("MJXB_DYN_SPEC", 1) != 0;
   m->tune.spec_max_rounds = env_int("MJXB_SPEC_MAX_ROUNDS", m->tune.spec_max_rounds);
   m->tune.skip_mid = env_int("MJXB_SKIP_MID", 1) != 0;
   m->tune.host_direct = env_int("MJXB_HOST_DIRECT", 1) != 0;
