@@ -299,8 +299,8 @@ def main():
                 "api": "mjxb_step_autoreset_host (pinned host buffers; one launch, action/keys streamed in behind ready flags, outputs stored into the caller's mapped buffers)"},
         "gpu_launches": gpu_launches,
         "gpu_launches_note": "counted by libmjxb.so (mjxb_launch_count) over the timed region: per step the schedule sort (batches >= 16,384 envs), the main tier and two overflow tiers that exit at once when their list is empty",
-        "kernels": ["mjxb_sort_work_kernel (work-sorted schedule: envs dealt to the CTAs by descending cost of their previous step, ~5 us)",
-                    "mjxb_step_kernel<false,32,16,16,true,true> (step: 32-row tile, 16 env-warps per SM, single-step instantiation)",
+        "kernels": ["mjxb_sort_work_kernel (work-sorted schedule: envs ordered by descending cost of their previous step, 2048-env segments)",
+                    "mjxb_step_kernel<false,32,16,16,true,true,true> (step: 32-row tile, 16 env-warps per SM, single-step instantiation, env groups taken from a device-wide counter)",
                     "mjxb_step_kernel<false,64,24,10,true,false> and <false,320,176,3,true,false> (overflow tiers; exit at once when their list is empty)"],
         "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                      "traffic": traffic, "algorithmic_bytes_per_launch": ALG_BYTES_PER_STEP * n, "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6650 (of fallback)",
