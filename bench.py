@@ -158,6 +158,7 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    numa_cpus = parallel.bind_to_gpu_numa(local_rank) if world > 1 and os.environ.get("MJXB_NO_NUMA_BIND") is None else 0
     torch.cuda.set_device(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
     if world > 1:
@@ -295,7 +296,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": config,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps, "numa_bound_cpus": numa_cpus,
                 "api": "mjxb_step_autoreset_host (pinned host buffers; one launch, action/keys streamed in behind ready flags, outputs stored into the caller's mapped buffers)"},
         "gpu_launches": gpu_launches,
         "gpu_launches_note": "counted by libmjxb.so (mjxb_launch_count) over the timed region: per step the schedule sort (batches >= 16,384 envs), the main tier and two overflow tiers that exit at once when their list is empty",

@@ -29,6 +29,26 @@ def init(backend: str) -> Tuple[int, int, int]:
     return rank, local_rank, world
 
 
+def bind_to_gpu_numa(local_rank: int) -> int:
+    """One process per GPU: restrict this process to the CPUs that are local to its GPU (NVML's ideal CPU affinity), so that pinned host
+    buffers (first touch) and the launching thread sit on the GPU's NUMA node. A launcher such as torchrun does not bind its workers;
+    with eight ranks the host-buffer path otherwise crosses the socket interconnect for part of the ranks. Call before the first CUDA /
+    pinned allocation. Returns the number of CPUs bound to (0: left as it was -- NVML missing, or the mask is empty / not allowed)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, ((os.cpu_count() or 64) + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
+
+
 def shard_range(n_total: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous env range [lo, hi) owned by `rank` (strong scaling: fixed total)."""
     base, rem = divmod(n_total, world)
